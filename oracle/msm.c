@@ -1,0 +1,130 @@
+/*
+ * msm.c -- Pippenger and Straus multiscalar multiplication, with the
+ * EdwardsPoint trait dispatch.  TEST INFRASTRUCTURE (oracle).
+ * Restates C/backend/serial/scalar_mul/{pippenger,straus,vartime_double_base}.rs
+ * and C/edwards.rs:966-1031.
+ */
+#include "oracle.h"
+#include <stdlib.h>
+#include <string.h>
+
+/* scalar_mul/pippenger.rs:67-160 */
+int msm_pippenger(ge_p3 *o, const uint8_t *scalars, const ge_p3 *points,
+                  const uint8_t *present, size_t n)
+{
+    unsigned w = n < 500 ? 6 : (n < 800 ? 7 : 8);                 /* :81-87 */
+    size_t max_digit = (size_t)1 << w;
+    size_t digits_count = scalar_to_radix_2w_size_hint(w);        /* :90 */
+    size_t buckets_count = max_digit / 2;                         /* :91 */
+
+    for (size_t i = 0; i < n; i++) if (present && !present[i]) return 0;   /* :101-104 None */
+
+    int8_t *digits = (int8_t *)malloc(64 * (n ? n : 1));
+    ge_pniels *pts = (ge_pniels *)malloc(sizeof(ge_pniels) * (n ? n : 1));
+    ge_p3 *buckets = (ge_p3 *)malloc(sizeof(ge_p3) * buckets_count);
+    for (size_t i = 0; i < n; i++) {
+        scalar_as_radix_2w(digits + 64 * i, scalars + 32 * i, w); /* :95 */
+        ge_p3_to_pniels(&pts[i], &points[i]);                     /* :97-99 */
+    }
+
+    ge_p3 total; int have_total = 0;
+    for (size_t di = digits_count; di-- > 0;) {                   /* :112, high column first */
+        for (size_t b = 0; b < buckets_count; b++) ge_identity(&buckets[b]);   /* :114-116 */
+        for (size_t i = 0; i < n; i++) {                          /* :122-136 */
+            int16_t digit = (int16_t)digits[64 * i + di];
+            ge_p1p1 r;
+            if (digit > 0) {
+                size_t b = (size_t)(digit - 1);
+                ge_add_pniels(&r, &buckets[b], &pts[i]); ge_p1p1_to_p3(&buckets[b], &r);
+            } else if (digit < 0) {
+                size_t b = (size_t)(-digit - 1);
+                ge_sub_pniels(&r, &buckets[b], &pts[i]); ge_p1p1_to_p3(&buckets[b], &r);
+            }
+        }
+        ge_p3 isum = buckets[buckets_count - 1], sum = buckets[buckets_count - 1];   /* :146-147 */
+        for (size_t i = buckets_count - 1; i-- > 0;) {            /* :148-151 */
+            ge_p3_add(&isum, &isum, &buckets[i]);
+            ge_p3_add(&sum, &sum, &isum);
+        }
+        if (!have_total) { total = sum; have_total = 1; }         /* :157 hi_column */
+        else { ge_p3 t; ge_mul_by_pow_2(&t, &total, w); ge_p3_add(&total, &t, &sum); }  /* :159 */
+    }
+    free(digits); free(pts); free(buckets);
+    *o = total;
+    return 1;
+}
+
+/* scalar_mul/straus.rs:159-200 */
+int msm_straus_vartime(ge_p3 *o, const uint8_t *scalars, const ge_p3 *points,
+                       const uint8_t *present, size_t n)
+{
+    for (size_t i = 0; i < n; i++) if (present && !present[i]) return 0;   /* :176-179 None */
+    int8_t *nafs = (int8_t *)malloc(256 * (n ? n : 1));
+    ge_naf_table5 *tabs = (ge_naf_table5 *)malloc(sizeof(ge_naf_table5) * (n ? n : 1));
+    for (size_t i = 0; i < n; i++) {
+        scalar_non_adjacent_form(nafs + 256 * i, scalars + 32 * i, 5);    /* :171-174 */
+        ge_naf_table5_from(&tabs[i], &points[i]);
+    }
+    ge_p2 r; ge_p2_identity(&r);                                  /* :181 */
+    for (int i = 255; i >= 0; i--) {                              /* :183-197 */
+        ge_p1p1 t; ge_p3 e;
+        ge_p2_double(&t, &r);
+        for (size_t j = 0; j < n; j++) {
+            int8_t d = nafs[256 * j + i];
+            if (d > 0) { ge_p1p1_to_p3(&e, &t); ge_add_pniels(&t, &e, &tabs[j].t[d / 2]); }
+            else if (d < 0) { ge_p1p1_to_p3(&e, &t); ge_sub_pniels(&t, &e, &tabs[j].t[(-d) / 2]); }
+        }
+        ge_p1p1_to_p2(&r, &t);
+    }
+    ge_p2_to_p3(o, &r);                                           /* :199 */
+    free(nafs); free(tabs);
+    return 1;
+}
+
+/* scalar_mul/straus.rs:103-144 */
+void msm_straus_ct(ge_p3 *o, const uint8_t *scalars, const ge_p3 *points, size_t n)
+{
+    ge_lookup_table *tabs = (ge_lookup_table *)malloc(sizeof(ge_lookup_table) * (n ? n : 1));
+    int8_t *digits = (int8_t *)malloc(64 * (n ? n : 1));
+    for (size_t i = 0; i < n; i++) {
+        ge_lookup_table_from(&tabs[i], &points[i]);               /* :114-117 */
+        scalar_as_radix_16(digits + 64 * i, scalars + 32 * i);    /* :123-126 */
+    }
+    ge_p3 Q; ge_identity(&Q);
+    for (int j = 63; j >= 0; j--) {                               /* :129-138 */
+        ge_mul_by_pow_2(&Q, &Q, 4);
+        for (size_t i = 0; i < n; i++) {
+            ge_pniels R; ge_p1p1 t;
+            ge_lookup_table_select(&R, &tabs[i], digits[64 * i + j]);
+            ge_add_pniels(&t, &Q, &R); ge_p1p1_to_p3(&Q, &t);
+        }
+    }
+    memset(digits, 0, 64 * (n ? n : 1));                          /* :140-141 zeroize */
+    free(tabs); free(digits);
+    *o = Q;
+}
+
+/* C/edwards.rs:1002-1030: size < 190 -> Straus, else Pippenger */
+int edwards_optional_multiscalar_mul(ge_p3 *o, const uint8_t *scalars, const ge_p3 *points,
+                                     const uint8_t *present, size_t n)
+{
+    if (n < 190) return msm_straus_vartime(o, scalars, points, present, n);
+    return msm_pippenger(o, scalars, points, present, n);
+}
+
+/* C/edwards.rs:970-995: always constant-time Straus */
+void edwards_multiscalar_mul(ge_p3 *o, const uint8_t *scalars, const ge_p3 *points, size_t n)
+{
+    msm_straus_ct(o, scalars, points, n);
+}
+
+/* value of scalar_mul/vartime_double_base.rs:23-72 (aA + bB); computed with the vartime
+ * Straus over [A, B], which yields the same group element */
+void edwards_vartime_double_scalar_mul_basepoint(ge_p3 *o, const uint8_t a[32], const ge_p3 *A,
+                                                 const uint8_t b[32])
+{
+    uint8_t sc[64]; ge_p3 pts[2];
+    memcpy(sc, a, 32); memcpy(sc + 32, b, 32);
+    pts[0] = *A; ge_basepoint(&pts[1]);
+    msm_straus_vartime(o, sc, pts, NULL, 2);
+}
