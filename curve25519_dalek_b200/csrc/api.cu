@@ -1,0 +1,257 @@
+// api.cu -- the extern "C" boundary of libdalek_b200.so (include/dalek_b200.h): context handling,
+// host<->device staging and the MSM entry points.  verify_batch lives in batch.cu, the
+// constant-time / Ristretto entry points in straus.cu.
+#include <cstring>
+#include <new>
+
+#include "../../include/dalek_b200.h"
+#include "engine.h"
+
+extern "C" {
+
+int dalek_b200_init(int device, dalek_b200_ctx **out)
+{
+    if (!out) return DALEK_E_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return DALEK_E_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DALEK_E_NO_DEVICE;
+    if (prop.major != 10) return DALEK_E_NO_DEVICE;   // built for sm_100a only; no fallback path
+    if (cudaSetDevice(device) != cudaSuccess) return DALEK_E_CUDA;
+    dalek_b200_ctx *ctx = new (std::nothrow) dalek_b200_ctx();
+    if (!ctx) return DALEK_E_NOMEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        delete ctx;
+        return DALEK_E_CUDA;
+    }
+    *out = ctx;
+    return DALEK_OK;
+}
+
+void dalek_b200_destroy(dalek_b200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream2);
+    DevBuf *bufs[] = {&ctx->scalars, &ctx->points_in, &ctx->points, &ctx->digits, &ctx->counts, &ctx->offsets,
+                      &ctx->sorted, &ctx->buckets, &ctx->red_a, &ctx->red_b, &ctx->red_c, &ctx->red_d,
+                      &ctx->result, &ctx->flags, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->misc3,
+                      &ctx->misc4, &ctx->misc5, &ctx->zs, &ctx->base_table};
+    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2);
+    delete ctx;
+}
+
+const char *dalek_b200_last_error(const dalek_b200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value)
+{
+    if (!ctx || !name) return DALEK_E_INVALID_ARG;
+    if (!strcmp(name, "window_bits")) { if (value != 0 && (value < 4 || value > 20)) return DALEK_E_INVALID_ARG; ctx->opt_window_bits = value; return 0; }
+    if (!strcmp(name, "verify_chunk")) { if (value < 1 || value > (1 << 20)) return DALEK_E_INVALID_ARG; ctx->opt_verify_chunk = value; return 0; }
+    return DALEK_E_INVALID_ARG;
+}
+
+uint64_t dalek_b200_launch_count(const dalek_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int dalek_b200_last_kernel_ms(const dalek_b200_ctx *ctx, float *ms, int *launches)
+{
+    if (!ctx) return DALEK_E_INVALID_ARG;
+    if (ms) *ms = ctx->last_kernel_ms;
+    if (launches) *launches = ctx->last_kernel_launches;
+    return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+static size_t point_in_bytes(int fmt) { return fmt == DALEK_POINTS_COMPRESSED ? 32 : 160; }
+
+// device scalars/points -> window sums in ctx->red? -> result.  Returns reference-level code.
+static int run_msm_dev(dalek_b200_ctx *ctx, const void *d_scalars, const void *d_points_in, int point_fmt, size_t n,
+                       size_t n_total, ge_p3_raw *d_windows, int *bad_out)
+{
+    int rc;
+    const int kind = point_fmt == DALEK_POINTS_COMPRESSED ? PK_NIELS : PK_PNIELS;
+    const size_t psz = kind == PK_NIELS ? sizeof(ge_niels_packed) : sizeof(ge_pniels_packed);
+    if ((rc = ws_reserve(ctx, ctx->points, std::max<size_t>(1, n) * psz))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->flags, 64))) return rc;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->flags.p, 0, 64, ctx->stream));
+    if ((rc = msm_prepare_points(ctx, d_points_in, point_fmt, n, ctx->points.p, (int *)ctx->flags.p))) return rc;
+    int c = msm_choose_window_bits(ctx, n_total);
+    if ((rc = msm_window_sums(ctx, (const uint32_t *)d_scalars, ctx->points.p, kind, n, c, d_windows))) return rc;
+    if (bad_out) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(bad_out, ctx->flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return 0;
+}
+
+static int finish_msm(dalek_b200_ctx *ctx, const ge_p3_raw *d_windows, int ranks, size_t n_total,
+                      uint8_t out_compressed[32], uint64_t out_limbs[20], uint32_t *is_identity)
+{
+    int rc;
+    int c = msm_choose_window_bits(ctx, n_total);
+    int nwin = msm_window_count_for_bits(c);
+    if ((rc = ws_reserve(ctx, ctx->result, sizeof(MsmResult)))) return rc;
+    if ((rc = msm_combine_windows(ctx, d_windows, ranks, nwin, c, (MsmResult *)ctx->result.p))) return rc;
+    if ((rc = pinned_reserve(ctx, sizeof(MsmResult) + 64))) return rc;
+    MsmResult *h = (MsmResult *)ctx->h_pinned;
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->result.p, sizeof(MsmResult), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
+    if (out_compressed) memcpy(out_compressed, h->compressed, 32);
+    if (out_limbs) memcpy(out_limbs, h->limbs, 160);
+    if (is_identity) *is_identity = h->is_identity;
+    return 0;
+}
+
+static int msm_common(dalek_b200_ctx *ctx, const void *scalars, const void *points, bool on_device, int point_fmt,
+                      size_t n, uint8_t out_compressed[32], uint64_t out_limbs[20])
+{
+    if (!ctx || (n && (!scalars || !points)) || (point_fmt != DALEK_POINTS_COMPRESSED && point_fmt != DALEK_POINTS_EXTENDED))
+        return DALEK_E_INVALID_ARG;
+    if (n >= (1ull << 31)) return DALEK_E_INVALID_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    const void *d_s = scalars, *d_p = points;
+    if (!on_device) {
+        if ((rc = ws_reserve(ctx, ctx->scalars, std::max<size_t>(1, n) * 32))) return rc;
+        if ((rc = ws_reserve(ctx, ctx->points_in, std::max<size_t>(1, n) * point_in_bytes(point_fmt)))) return rc;
+        if (n) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->points_in.p, points, n * point_in_bytes(point_fmt), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        d_s = ctx->scalars.p; d_p = ctx->points_in.p;
+    }
+    int c = msm_choose_window_bits(ctx, n);
+    int nwin = msm_window_count_for_bits(c);
+    if ((rc = ws_reserve(ctx, ctx->misc0, (size_t)nwin * sizeof(ge_p3_raw)))) return rc;
+    if ((rc = pinned_reserve(ctx, sizeof(MsmResult) + 64))) return rc;
+    int *h_bad = (int *)((char *)ctx->h_pinned + sizeof(MsmResult));
+    *h_bad = 0;
+    if ((rc = run_msm_dev(ctx, d_s, d_p, point_fmt, n, n, (ge_p3_raw *)ctx->misc0.p, h_bad))) return rc;
+    if ((rc = finish_msm(ctx, (const ge_p3_raw *)ctx->misc0.p, 1, n, out_compressed, out_limbs, nullptr))) return rc;
+    return *h_bad ? DALEK_NONE : DALEK_OK;
+}
+
+extern "C" {
+
+int dalek_b200_edwards_vartime_msm(dalek_b200_ctx *ctx, const uint8_t *scalars, const void *points, int point_fmt,
+                                   size_t n, uint8_t out_compressed[32], uint64_t out_limbs[20])
+{
+    return msm_common(ctx, scalars, points, false, point_fmt, n, out_compressed, out_limbs);
+}
+
+int dalek_b200_edwards_vartime_msm_dev(dalek_b200_ctx *ctx, const void *d_scalars, const void *d_points, int point_fmt,
+                                       size_t n, uint8_t out_compressed[32], uint64_t out_limbs[20])
+{
+    return msm_common(ctx, d_scalars, d_points, true, point_fmt, n, out_compressed, out_limbs);
+}
+
+int dalek_b200_msm_window_count(dalek_b200_ctx *ctx, size_t n_total)
+{
+    if (!ctx) return DALEK_E_INVALID_ARG;
+    return msm_window_count_for_bits(msm_choose_window_bits(ctx, n_total));
+}
+
+static int partial_common(dalek_b200_ctx *ctx, const void *scalars, const void *points, bool on_device, int point_fmt,
+                          size_t n_local, size_t n_total, uint64_t *out_windows);
+
+int dalek_b200_edwards_msm_partial(dalek_b200_ctx *ctx, const uint8_t *scalars, const void *points, int point_fmt,
+                                   size_t n_local, size_t n_total, uint64_t *out_windows)
+{
+    return partial_common(ctx, scalars, points, false, point_fmt, n_local, n_total, out_windows);
+}
+
+int dalek_b200_edwards_msm_partial_dev(dalek_b200_ctx *ctx, const void *d_scalars, const void *d_points, int point_fmt,
+                                       size_t n_local, size_t n_total, uint64_t *out_windows)
+{
+    return partial_common(ctx, d_scalars, d_points, true, point_fmt, n_local, n_total, out_windows);
+}
+
+}  // extern "C"
+
+// window accumulators cross the boundary as canonical radix-2^51 limbs (20 u64 each)
+__global__ void k_windows_to_limbs(const ge_p3_raw *__restrict__ win, int nwin, uint64_t *__restrict__ out)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwin) return;
+    ge_p3 p; ge_p3_raw r = win[w]; ge_p3_load_raw(p, r);
+    fe_to_limbs51(out + 20 * w, p.X); fe_to_limbs51(out + 20 * w + 5, p.Y);
+    fe_to_limbs51(out + 20 * w + 10, p.Z); fe_to_limbs51(out + 20 * w + 15, p.T);
+}
+__global__ void k_limbs_to_windows(const uint64_t *__restrict__ in, int count, ge_p3_raw *__restrict__ win)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= count) return;
+    ge_p3 p;
+    fe_from_limbs51(p.X, in + 20 * w); fe_from_limbs51(p.Y, in + 20 * w + 5);
+    fe_from_limbs51(p.Z, in + 20 * w + 10); fe_from_limbs51(p.T, in + 20 * w + 15);
+    ge_p3_raw r; ge_p3_store_raw(r, p); win[w] = r;
+}
+
+static int partial_common(dalek_b200_ctx *ctx, const void *scalars, const void *points, bool on_device, int point_fmt,
+                          size_t n_local, size_t n_total, uint64_t *out_windows)
+{
+    if (!ctx || !out_windows || (n_local && (!scalars || !points)) || n_local > n_total ||
+        (point_fmt != DALEK_POINTS_COMPRESSED && point_fmt != DALEK_POINTS_EXTENDED) || n_local >= (1ull << 31))
+        return DALEK_E_INVALID_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    const void *d_s = scalars, *d_p = points;
+    if (!on_device) {
+        if ((rc = ws_reserve(ctx, ctx->scalars, std::max<size_t>(1, n_local) * 32))) return rc;
+        if ((rc = ws_reserve(ctx, ctx->points_in, std::max<size_t>(1, n_local) * point_in_bytes(point_fmt)))) return rc;
+        if (n_local) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n_local * 32, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->points_in.p, points, n_local * point_in_bytes(point_fmt), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        d_s = ctx->scalars.p; d_p = ctx->points_in.p;
+    }
+    int c = msm_choose_window_bits(ctx, n_total);
+    int nwin = msm_window_count_for_bits(c);
+    if ((rc = ws_reserve(ctx, ctx->misc0, (size_t)nwin * sizeof(ge_p3_raw)))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->misc1, (size_t)nwin * 160))) return rc;
+    if ((rc = pinned_reserve(ctx, (size_t)nwin * 160 + 64))) return rc;
+    int *h_bad = (int *)((char *)ctx->h_pinned + (size_t)nwin * 160);
+    *h_bad = 0;
+    if ((rc = run_msm_dev(ctx, d_s, d_p, point_fmt, n_local, n_total, (ge_p3_raw *)ctx->misc0.p, h_bad))) return rc;
+    k_windows_to_limbs<<<(nwin + 63) / 64, 64, 0, ctx->stream>>>((const ge_p3_raw *)ctx->misc0.p, nwin, (uint64_t *)ctx->misc1.p);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->misc1.p, (size_t)nwin * 160, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
+    memcpy(out_windows, ctx->h_pinned, (size_t)nwin * 160);
+    return *h_bad ? DALEK_NONE : DALEK_OK;
+}
+
+extern "C" int dalek_b200_edwards_msm_combine(dalek_b200_ctx *ctx, const uint64_t *windows, int ranks, size_t n_total,
+                                              uint8_t out_compressed[32], uint64_t out_limbs[20])
+{
+    if (!ctx || !windows || ranks < 1 || ranks > 1024) return DALEK_E_INVALID_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    int c = msm_choose_window_bits(ctx, n_total);
+    int nwin = msm_window_count_for_bits(c);
+    size_t cnt = (size_t)ranks * nwin;
+    if ((rc = ws_reserve(ctx, ctx->misc1, cnt * 160))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->misc0, cnt * sizeof(ge_p3_raw)))) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->misc1.p, windows, cnt * 160, cudaMemcpyHostToDevice, ctx->stream));
+    k_limbs_to_windows<<<(unsigned)((cnt + 63) / 64), 64, 0, ctx->stream>>>((const uint64_t *)ctx->misc1.p, (int)cnt, (ge_p3_raw *)ctx->misc0.p);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+    return finish_msm(ctx, (const ge_p3_raw *)ctx->misc0.p, ranks, n_total, out_compressed, out_limbs, nullptr);
+}

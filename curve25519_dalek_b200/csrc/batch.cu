@@ -1,0 +1,330 @@
+// batch.cu -- ed25519_dalek::verify_batch (ed25519-dalek/src/batch.rs:146-251) on one B200.
+//
+//   k_hram        one thread per signature: SHA-512(R || A || M) (batch.rs:179-191), h_i = hash mod l
+//                 (batch.rs:213-216), canonical-s check (batch.rs:208-211, signature.rs:89-94)
+//   k_transcript  one thread per chunk of `verify_chunk` signatures: the Merlin transcript of
+//                 batch.rs:168-205 and the 16-byte z_i draws of batch.rs:219-222
+//   k_coeffs      one thread per signature: z_i*s_i and z_i*h_i mod l (batch.rs:225-233)
+//   k_sum_*       B_coefficient = sum z_i s_i, negated (batch.rs:225-230, :241)
+//   k_prep_*      R_i / A_i decompression (batch.rs:235-236, verifying.rs:167-175) into Niels form
+//   then the (2n+1)-term bucket MSM of msm.cu (batch.rs:240-244) and the identity test (:246-250).
+//
+// HBM layout: signatures n x 64 B (R || s), keys n x 32 B, messages back to back with n+1 u64
+// offsets; hrams n x 64 B; scalars (2n+1) x 32 B = [-sum z_i s_i, z_1..z_n, z_1 h_1..z_n h_n];
+// points (2n+1) x 96 B Niels = [B, R_1..R_n, A_1..A_n]  (same order as batch.rs:240-244).
+#include <algorithm>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../include/dalek_b200.h"
+#include "engine.h"
+#include "hash.cuh"
+#include "sc.cuh"
+
+static inline unsigned cdiv(size_t a, unsigned b) { return (unsigned)((a + b - 1) / b); }
+
+enum { FLAG_BAD_A = 0, FLAG_BAD_S = 1, FLAG_BAD_R = 2 };
+
+__global__ void __launch_bounds__(128)
+k_hram(const uint8_t *__restrict__ msgs, const uint64_t *__restrict__ offs, const uint32_t *__restrict__ sigs,
+       const uint32_t *__restrict__ keys, size_t n, uint32_t *__restrict__ hrams, uint32_t *__restrict__ hs,
+       int *__restrict__ flags)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t R[8], A[8], s[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { R[k] = sigs[16 * i + k]; s[k] = sigs[16 * i + 8 + k]; A[k] = keys[8 * i + k]; }
+    sha512_state st;
+    sha512_init(st);
+    sha512_update_words(st, R);
+    sha512_update_words(st, A);
+    uint64_t lo = offs[i], hi = offs[i + 1];
+    sha512_update(st, msgs + lo, (size_t)(hi - lo));
+    uint32_t dig[16];
+    sha512_final_words(st, dig);
+#pragma unroll
+    for (int k = 0; k < 16; k++) hrams[16 * i + k] = dig[k];
+    uint32_t h[8];
+    sc_reduce512(h, dig);
+#pragma unroll
+    for (int k = 0; k < 8; k++) hs[8 * i + k] = h[k];
+    if (!sc_is_canonical(s)) atomicOr(&flags[FLAG_BAD_S], 1);
+}
+
+__global__ void __launch_bounds__(64)
+k_transcript(const uint32_t *__restrict__ hrams, const uint32_t *__restrict__ sigs, size_t n, uint32_t chunk,
+             uint32_t *__restrict__ zs)
+{
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t lo = t * chunk;
+    if (lo >= n) return;
+    size_t hi = min(lo + (size_t)chunk, n);
+    strobe128 s;
+    strobe_init(s, (const uint8_t *)"Merlin v1.0", 11);                                  // batch.rs:44, transcript.rs:56
+    {   // append_message(b"dom-sep", b"ed25519 batch verification")  (transcript.rs:58, batch.rs:168)
+        const uint8_t *lab = (const uint8_t *)"dom-sep";
+        const uint8_t *msg = (const uint8_t *)"ed25519 batch verification";
+        strobe_begin_op(s, SFLAG_M | SFLAG_A);
+        for (int k = 0; k < 7; k++) strobe_absorb_byte(s, lab[k]);
+        strobe_absorb_byte(s, 26); strobe_absorb_byte(s, 0); strobe_absorb_byte(s, 0); strobe_absorb_byte(s, 0);
+        strobe_begin_op(s, SFLAG_A);
+        for (int k = 0; k < 26; k++) strobe_absorb_byte(s, msg[k]);
+    }
+    for (size_t i = lo; i < hi; i++) merlin_append_words(s, (const uint8_t *)"hram", 4, hrams + 16 * i, 64);      // batch.rs:195-197
+    for (size_t i = lo; i < hi; i++) merlin_append_words(s, (const uint8_t *)"sig.s", 5, sigs + 16 * i + 8, 32);  // batch.rs:199-201
+    // build_rng().finalize(&mut ZeroRng): meta_ad("rng"), key(32 zero bytes)  (transcript.rs:157-173)
+    strobe_begin_op(s, SFLAG_M | SFLAG_A);
+    strobe_absorb_byte(s, 'r'); strobe_absorb_byte(s, 'n'); strobe_absorb_byte(s, 'g');
+    strobe_begin_op(s, SFLAG_A | SFLAG_C);
+    for (int k = 0; k < 32; k++) { strobe_set_byte(s, s.pos, 0); if (++s.pos == STROBE_R) strobe_run_f(s); }
+    for (size_t i = lo; i < hi; i++) {
+        // TranscriptRng::try_fill_bytes(16): meta_ad(16u32), prf(16)  (transcript.rs:200-206)
+        strobe_begin_op(s, SFLAG_M | SFLAG_A);
+        strobe_absorb_byte(s, 16); strobe_absorb_byte(s, 0); strobe_absorb_byte(s, 0); strobe_absorb_byte(s, 0);
+        strobe_begin_op(s, SFLAG_I | SFLAG_A | SFLAG_C);
+        uint32_t z[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 16; k++) {
+            z[k >> 2] |= strobe_get_byte(s, s.pos) << (8 * (k & 3));
+            strobe_set_byte(s, s.pos, 0);
+            if (++s.pos == STROBE_R) strobe_run_f(s);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) zs[4 * i + k] = z[k];
+    }
+}
+
+// scalars[0] is written by k_sum_final; scalars[1+i] = z_i; scalars[1+n+i] = z_i h_i; zs_prod[i] = z_i s_i
+__global__ void __launch_bounds__(128)
+k_coeffs(const uint32_t *__restrict__ zs, const uint32_t *__restrict__ sigs, const uint32_t *__restrict__ hs, size_t n,
+         uint32_t *__restrict__ scalars, uint32_t *__restrict__ zs_prod)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t z[8], s[8], h[8], r[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { z[k] = zs[4 * i + k]; z[4 + k] = 0; }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { s[k] = sigs[16 * i + 8 + k]; h[k] = hs[8 * i + k]; }
+#pragma unroll
+    for (int k = 0; k < 8; k++) scalars[8 * (1 + i) + k] = z[k];
+    sc_mul(r, z, h);
+#pragma unroll
+    for (int k = 0; k < 8; k++) scalars[8 * (1 + n + i) + k] = r[k];
+    sc_mul(r, z, s);
+#pragma unroll
+    for (int k = 0; k < 8; k++) zs_prod[8 * i + k] = r[k];
+}
+
+// plain multiword sums (values < l, at most 2^31 of them: 9 words are enough)
+__global__ void k_sum_partial(const uint32_t *__restrict__ v, size_t n, uint32_t nthreads, uint32_t *__restrict__ partial)
+{
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    uint32_t acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) acc[k] = 0;
+    for (size_t i = t; i < n; i += nthreads) {
+        uint64_t carry = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { uint64_t x = (uint64_t)acc[k] + v[8 * i + k] + carry; acc[k] = (uint32_t)x; carry = x >> 32; }
+        acc[8] += (uint32_t)carry;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) partial[9 * t + k] = acc[k];
+}
+
+__global__ void k_sum_final(const uint32_t *__restrict__ partial, uint32_t count, uint32_t *__restrict__ scalars0)
+{
+    __shared__ uint32_t sh[256][10];
+    uint32_t acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) acc[k] = 0;
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
+        uint64_t carry = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) { uint64_t x = (uint64_t)acc[k] + partial[9 * i + k] + carry; acc[k] = (uint32_t)x; carry = x >> 32; }
+        acc[9] += (uint32_t)carry;
+    }
+#pragma unroll
+    for (int k = 0; k < 10; k++) sh[threadIdx.x][k] = acc[k];
+    __syncthreads();
+    for (uint32_t d = blockDim.x / 2; d > 0; d >>= 1) {
+        if (threadIdx.x < d) {
+            uint64_t carry = 0;
+            for (int k = 0; k < 10; k++) {
+                uint64_t x = (uint64_t)sh[threadIdx.x][k] + sh[threadIdx.x + d][k] + carry;
+                sh[threadIdx.x][k] = (uint32_t)x; carry = x >> 32;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint32_t x[16], r[8], neg[8];
+        for (int k = 0; k < 16; k++) x[k] = k < 10 ? sh[0][k] : 0;
+        sc_reduce512(r, x);
+        sc_neg(neg, r);                                   // -B_coefficient (batch.rs:241)
+        for (int k = 0; k < 8; k++) scalars0[k] = neg[k];
+    }
+}
+
+// decompress R_i (stride 64 B inside the signature) and A_i into the point array; slot 0 = basepoint
+__global__ void __launch_bounds__(128)
+k_prep_RA(const uint32_t *__restrict__ sigs, const uint32_t *__restrict__ keys, size_t n,
+          ge_niels_packed *__restrict__ points, int *__restrict__ flags)
+{
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > 2 * n) return;
+    fe x, y;
+    if (j == 0) {
+        fe_const_base_x(x); fe_const_base_y(y);
+    } else {
+        uint32_t s[8];
+        bool isR = j <= n;
+        const uint32_t *src = isR ? sigs + 16 * (j - 1) : keys + 8 * (j - 1 - n);
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = src[k];
+        if (!ge_decompress_affine(x, y, s)) {
+            atomicOr(&flags[isR ? FLAG_BAD_R : FLAG_BAD_A], 1);
+            fe_0(x); fe_1(y);
+        }
+    }
+    ge_niels nl; ge_affine_to_niels(nl, x, y);
+    ge_niels_packed p; ge_niels_pack(p, nl);
+    uint4 *o = reinterpret_cast<uint4 *>(points + j);
+#pragma unroll
+    for (int k = 0; k < 6; k++) o[k] = make_uint4(p.w[4 * k], p.w[4 * k + 1], p.w[4 * k + 2], p.w[4 * k + 3]);
+}
+
+// ------------------------------------------------------------------------------------------
+static int verify_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t *d_offs, const uint32_t *d_sigs,
+                      const uint32_t *d_keys, size_t n)
+{
+    int rc;
+    cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+    const size_t m = 2 * n + 1;
+    if (m >= (1ull << 31)) return DALEK_E_INVALID_ARG;
+    uint32_t chunk = (uint32_t)ctx->opt_verify_chunk;
+    if ((rc = ws_reserve(ctx, ctx->misc2, std::max<size_t>(1, n) * 64))) return rc;   // hrams
+    if ((rc = ws_reserve(ctx, ctx->misc3, std::max<size_t>(1, n) * 32))) return rc;   // h_i
+    if ((rc = ws_reserve(ctx, ctx->misc4, std::max<size_t>(1, n) * 32))) return rc;   // z_i s_i
+    if ((rc = ws_reserve(ctx, ctx->zs, std::max<size_t>(1, n) * 16))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->scalars, m * 32))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->points, m * sizeof(ge_niels_packed)))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->flags, 64))) return rc;
+    const uint32_t nsum = 4096;
+    if ((rc = ws_reserve(ctx, ctx->misc5, (size_t)nsum * 9 * 4))) return rc;
+    int *flags = (int *)ctx->flags.p;
+    uint32_t *scalars = (uint32_t *)ctx->scalars.p;
+    CUDA_TRY(ctx, cudaMemsetAsync(flags, 0, 64, st));
+    // decompression runs on the second stream, concurrently with hashing / transcript / coefficients
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
+    k_prep_RA<<<cdiv(m, 128), 128, 0, st2>>>(d_sigs, d_keys, n, (ge_niels_packed *)ctx->points.p, flags);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, st2));
+    if (n) {
+        k_hram<<<cdiv(n, 128), 128, 0, st>>>(d_msgs, d_offs, d_sigs, d_keys, n, (uint32_t *)ctx->misc2.p,
+                                             (uint32_t *)ctx->misc3.p, flags);
+        size_t nchunks = (n + chunk - 1) / chunk;
+        k_transcript<<<cdiv(nchunks, 64), 64, 0, st>>>((const uint32_t *)ctx->misc2.p, d_sigs, n, chunk, (uint32_t *)ctx->zs.p);
+        k_coeffs<<<cdiv(n, 128), 128, 0, st>>>((const uint32_t *)ctx->zs.p, d_sigs, (const uint32_t *)ctx->misc3.p, n,
+                                               scalars, (uint32_t *)ctx->misc4.p);
+        ctx->launches += 3;
+    }
+    k_sum_partial<<<cdiv(nsum, 128), 128, 0, st>>>((const uint32_t *)ctx->misc4.p, n, nsum, (uint32_t *)ctx->misc5.p);
+    k_sum_final<<<1, 256, 0, st>>>((const uint32_t *)ctx->misc5.p, nsum, scalars);
+    ctx->launches += 2;
+    ctx->last_zs_n = n;
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    // the (2n+1)-term MSM (batch.rs:240-244)
+    int c = msm_choose_window_bits(ctx, m);
+    int nwin = msm_window_count_for_bits(c);
+    if ((rc = ws_reserve(ctx, ctx->misc0, (size_t)nwin * sizeof(ge_p3_raw)))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->result, sizeof(MsmResult)))) return rc;
+    if ((rc = msm_window_sums(ctx, scalars, ctx->points.p, PK_NIELS, m, c, (ge_p3_raw *)ctx->misc0.p))) return rc;
+    if ((rc = msm_combine_windows(ctx, (const ge_p3_raw *)ctx->misc0.p, 1, nwin, c, (MsmResult *)ctx->result.p))) return rc;
+    if ((rc = pinned_reserve(ctx, sizeof(MsmResult) + 128))) return rc;
+    MsmResult *h = (MsmResult *)ctx->h_pinned;
+    int *hflags = (int *)((char *)ctx->h_pinned + sizeof(MsmResult));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->result.p, sizeof(MsmResult), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
+    // error precedence follows the reference: VerifyingKey::from_bytes happens before verify_batch
+    // can be called (PointDecompression); then s canonicity (batch.rs:208-211); then R / equation.
+    if (hflags[FLAG_BAD_A]) return ED25519_ERR_POINT_DECOMPRESSION;
+    if (hflags[FLAG_BAD_S]) return ED25519_ERR_SCALAR_FORMAT;
+    if (hflags[FLAG_BAD_R]) return ED25519_ERR_VERIFY;
+    return h->is_identity ? DALEK_OK : ED25519_ERR_VERIFY;
+}
+
+extern "C" {
+
+int ed25519_b200_verify_batch_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat, const void *d_msg_offsets,
+                                       const void *d_sigs, const void *d_pubkeys, size_t n, size_t msgs_bytes)
+{
+    (void)msgs_bytes;
+    if (!ctx || (n && (!d_msg_offsets || !d_sigs || !d_pubkeys))) return DALEK_E_INVALID_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return verify_dev(ctx, (const uint8_t *)d_msgs_flat, (const uint64_t *)d_msg_offsets, (const uint32_t *)d_sigs,
+                      (const uint32_t *)d_pubkeys, n);
+}
+
+int ed25519_b200_verify_batch_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint64_t *msg_offsets,
+                                   const uint8_t *sigs, const uint8_t *pubkeys, size_t n)
+{
+    if (!ctx || (n && (!msg_offsets || !sigs || !pubkeys))) return DALEK_E_INVALID_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    size_t mbytes = n ? (size_t)msg_offsets[n] : 0;
+    if (n && msg_offsets[0] != 0) return DALEK_E_INVALID_ARG;
+    if ((rc = ws_reserve(ctx, ctx->misc1, mbytes + 16))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->red_a, (n + 1) * 8))) return rc;          // offsets (reduction scratch is idle here)
+    if ((rc = ws_reserve(ctx, ctx->points_in, std::max<size_t>(1, n) * 96))) return rc;   // sigs + keys
+    uint8_t *d_sigs = (uint8_t *)ctx->points_in.p, *d_keys = d_sigs + n * 64;
+    if (n) {
+        if (mbytes) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->misc1.p, msgs_flat, mbytes, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->red_a.p, msg_offsets, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_sigs, sigs, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_keys, pubkeys, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // red_a is reused by the MSM reduction later in the same stream; the offsets are only read by
+    // k_hram, which is ordered before it.
+    return verify_dev(ctx, (const uint8_t *)ctx->misc1.p, (const uint64_t *)ctx->red_a.p, (const uint32_t *)d_sigs,
+                      (const uint32_t *)d_keys, n);
+}
+
+int ed25519_b200_verify_batch(dalek_b200_ctx *ctx, const uint8_t *const *msgs, const size_t *msg_lens,
+                              const uint8_t *sigs, const uint8_t *pubkeys, size_t n)
+{
+    if (!ctx || (n && (!msgs || !msg_lens || !sigs || !pubkeys))) return DALEK_E_INVALID_ARG;
+    // gather the messages into one staging buffer (multi-threaded for large batches)
+    std::vector<uint64_t> offs(n + 1);
+    offs[0] = 0;
+    for (size_t i = 0; i < n; i++) offs[i + 1] = offs[i] + msg_lens[i];
+    std::vector<uint8_t> flat(offs[n] + 1);
+    unsigned nt = n > (1u << 16) ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    auto work = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) if (msg_lens[i]) memcpy(flat.data() + offs[i], msgs[i], msg_lens[i]);
+    };
+    if (nt <= 1) work(0, n);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++) th.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+        for (auto &x : th) x.join();
+    }
+    return ed25519_b200_verify_batch_flat(ctx, flat.data(), offs.data(), sigs, pubkeys, n);
+}
+
+int ed25519_b200_last_zs(dalek_b200_ctx *ctx, uint8_t *zs_out, size_t n)
+{
+    if (!ctx || !zs_out || n > ctx->last_zs_n) return DALEK_E_INVALID_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n) CUDA_TRY(ctx, cudaMemcpy(zs_out, ctx->zs.p, n * 16, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// engine.h -- internal (C++) interface between the translation units of libdalek_b200.so.
+// The public boundary is include/dalek_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "ge.cuh"
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct dalek_b200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    std::string last_error;
+    uint64_t launches = 0;
+    // options
+    long opt_window_bits = 0;
+    long opt_verify_chunk = 128;
+    // timing of the dominant kernel in the last call
+    float last_kernel_ms = 0.f;
+    int last_kernel_launches = 0;
+    // device workspaces (grown on demand, reused across calls)
+    DevBuf scalars, points_in, points, digits, counts, offsets, sorted, buckets, red_a, red_b, red_c,
+        red_d, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table;
+    bool base_table_ready = false;
+    // pinned host staging
+    void *h_pinned = nullptr;
+    size_t h_pinned_cap = 0;
+    size_t last_zs_n = 0;
+};
+
+#define CUDA_TRY(ctx, expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);              \
+            return -3;                                                                           \
+        }                                                                                        \
+    } while (0)
+
+int ws_reserve(dalek_b200_ctx *ctx, DevBuf &b, size_t bytes);
+int pinned_reserve(dalek_b200_ctx *ctx, size_t bytes);
+
+// ---- point preparation (msm.cu) ----
+// kinds of device point arrays fed to the bucket kernels
+enum { PK_NIELS = 0 /* ge_niels_packed, 96 B */, PK_PNIELS = 1 /* ge_pniels_packed, 128 B */ };
+
+// Convert n input points (device memory, format DALEK_POINTS_*) into packed Niels form.
+// Compressed inputs give PK_NIELS and set *d_bad (device int) nonzero if any fails to decode;
+// extended inputs give PK_PNIELS.
+int msm_prepare_points(dalek_b200_ctx *ctx, const void *d_in, int point_fmt, size_t n, void *d_out,
+                       int *d_bad);
+
+// Window width (bits) the engine uses for an MSM over n pairs.
+int msm_choose_window_bits(const dalek_b200_ctx *ctx, size_t n);
+int msm_window_count_for_bits(int c);
+
+// Bucket MSM over device inputs: writes `nwin` window accumulators (raw p3) to d_windows.
+int msm_window_sums(dalek_b200_ctx *ctx, const uint32_t *d_scalars /* n x 8 words */, const void *d_points,
+                    int point_kind, size_t n, int c, ge_p3_raw *d_windows);
+// total = sum over ranks of windows, Horner-combined; writes compressed (8 words) + canonical
+// limbs51 (20 u64) + identity flag to d_result (layout: 8 u32 | pad | 20 u64 | u32 flag).
+struct MsmResult { uint32_t compressed[8]; uint64_t limbs[20]; uint32_t is_identity; uint32_t pad; };
+int msm_combine_windows(dalek_b200_ctx *ctx, const ge_p3_raw *d_windows, int ranks, int nwin, int c,
+                        MsmResult *d_result);
+
+// ---- constant-time Straus (straus.cu) ----
+int straus_ct_msm(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points_pniels, size_t n,
+                  MsmResult *d_result);
+int ristretto_double_base(dalek_b200_ctx *ctx, const uint8_t *d_a, const uint8_t *d_b, const uint8_t G[32],
+                          const uint8_t H[32], size_t n, uint8_t *d_out, int *h_status);

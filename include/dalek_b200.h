@@ -1,0 +1,172 @@
+/*
+ * dalek_b200.h -- C ABI of the B200 multiscalar-multiplication / batch-verification engine.
+ *
+ * The reference (curve25519-dalek / ed25519-dalek, 100 % Rust) has no FFI for this path: the
+ * hot path sits behind Rust traits.  Each entry point below replaces one of those trait
+ * methods / functions and names it (paths relative to the reference tree):
+ *
+ *   C/ = curve25519-dalek/src/   E/ = ed25519-dalek/src/
+ *
+ * A thin Rust shim (shown in INTEGRATION.md) collects the trait iterators into the flat
+ * buffers used here.  All buffers are caller-owned; unless a `_dev` variant is named, pointers
+ * are HOST pointers and the call copies them to the device, runs, copies the result back and
+ * returns (blocking).  A context may be used by one thread at a time; different contexts may
+ * be used concurrently.
+ *
+ * Data formats
+ *   scalar            32 bytes little-endian, any value < 2^256 (the reference's Scalar
+ *                     invariant is bit 255 clear, C/scalar.rs:193-230; not required here)
+ *   compressed point  32 bytes CompressedEdwardsY (C/edwards.rs:175) or CompressedRistretto
+ *   extended point    20 x uint64_t: X, Y, Z, T as FieldElement51 radix-2^51 limbs
+ *                     (C/edwards.rs:390-395, C/backend/serial/u64/field.rs:43); limbs < 2^54
+ *
+ * Return codes: 0 = success / Ok; positive = the reference's own error values (see the
+ * DALEK_* constants); negative = engine errors (bad argument, CUDA failure).  There is no CPU
+ * fallback: without a usable CUDA device dalek_b200_init fails with DALEK_E_NO_DEVICE.
+ */
+#ifndef DALEK_B200_H
+#define DALEK_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dalek_b200_ctx dalek_b200_ctx;
+
+/* reference-level outcomes */
+#define DALEK_OK 0
+#define DALEK_NONE 1                      /* Option::None: a point failed to decompress (C/traits.rs:196) */
+#define ED25519_ERR_VERIFY 1              /* InternalError::Verify             (E/errors.rs:38) */
+#define ED25519_ERR_ARRAY_LENGTH 2        /* InternalError::ArrayLength        (E/errors.rs:41-49) */
+#define ED25519_ERR_SCALAR_FORMAT 3       /* InternalError::ScalarFormat       (E/errors.rs:27) */
+#define ED25519_ERR_POINT_DECOMPRESSION 4 /* InternalError::PointDecompression (E/errors.rs:26) */
+/* engine errors */
+#define DALEK_E_INVALID_ARG (-1)
+#define DALEK_E_NO_DEVICE (-2)
+#define DALEK_E_CUDA (-3)
+#define DALEK_E_NOMEM (-4)
+
+#define DALEK_POINTS_COMPRESSED 0         /* n x 32 B CompressedEdwardsY */
+#define DALEK_POINTS_EXTENDED 1           /* n x 20 x u64 radix-2^51 limbs */
+
+/* -------- context ---------------------------------------------------------------------- */
+/* Create an engine context on CUDA device `device`.  Fails (no CPU fallback) if the device
+ * is missing or is not an sm_100 part. */
+int dalek_b200_init(int device, dalek_b200_ctx **out);
+void dalek_b200_destroy(dalek_b200_ctx *ctx);
+const char *dalek_b200_last_error(const dalek_b200_ctx *ctx);
+/* Tunables: "window_bits" (0 = choose from n), "verify_chunk" (transcript chunk, default 128),
+ * Returns 0 or DALEK_E_INVALID_ARG. */
+int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value);
+/* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
+uint64_t dalek_b200_launch_count(const dalek_b200_ctx *ctx);
+/* Milliseconds (CUDA events on the context's stream) spent in the dominant kernel of the last
+ * call (bucket accumulation for MSM calls), and that kernel's launch count in the last call. */
+int dalek_b200_last_kernel_ms(const dalek_b200_ctx *ctx, float *ms, int *launches);
+
+/* -------- EdwardsPoint multiscalar multiplication --------------------------------------- */
+/*
+ * VartimeMultiscalarMul::optional_multiscalar_mul / vartime_multiscalar_mul for EdwardsPoint
+ * (C/traits.rs:196-262, C/edwards.rs:1002-1030; algorithms C/backend/serial/scalar_mul/
+ * pippenger.rs:67-160 and straus.rs:159-200).  Computes sum scalars[i] * points[i].
+ * Returns DALEK_NONE when point_fmt is COMPRESSED and any point fails to decompress
+ * (the reference returns None when any Option<Point> is None).  n = 0 yields the identity.
+ * out_compressed receives the 32-byte CompressedEdwardsY of the result (EdwardsPoint::compress,
+ * C/edwards.rs:564-617); out_limbs (nullable) receives canonical radix-2^51 X,Y,Z,T limbs of an
+ * equal point (projectively equal to the reference's result; limb values themselves differ
+ * between the reference's own backends).
+ */
+int dalek_b200_edwards_vartime_msm(dalek_b200_ctx *ctx, const uint8_t *scalars, const void *points,
+                                   int point_fmt, size_t n, uint8_t out_compressed[32],
+                                   uint64_t out_limbs[20]);
+/*
+ * MultiscalarMul::multiscalar_mul for EdwardsPoint (constant-time contract, C/traits.rs:78-134,
+ * C/edwards.rs:970-995, straus.rs:103-144): uniform control flow and table scans that do not
+ * depend on the scalars.  Points must all be valid (the trait takes points, not Options):
+ * an undecodable compressed point is DALEK_E_INVALID_ARG.
+ */
+int dalek_b200_edwards_ct_msm(dalek_b200_ctx *ctx, const uint8_t *scalars, const void *points,
+                              int point_fmt, size_t n, uint8_t out_compressed[32],
+                              uint64_t out_limbs[20]);
+/* Same two calls with device-resident inputs (scalars: n x 32 B; points as point_fmt says);
+ * outputs are still written to host memory. */
+int dalek_b200_edwards_vartime_msm_dev(dalek_b200_ctx *ctx, const void *d_scalars, const void *d_points,
+                                       int point_fmt, size_t n, uint8_t out_compressed[32],
+                                       uint64_t out_limbs[20]);
+
+/* -------- sharded MSM (one call per GPU / rank) -------------------------------- */
+/* Number of window accumulators a partial MSM over `n_total` pairs produces (all ranks must
+ * pass the same n_total so that the window width agrees). */
+int dalek_b200_msm_window_count(dalek_b200_ctx *ctx, size_t n_total);
+/* Partial MSM over this rank's shard: writes `window_count` window accumulators
+ * (each 20 x u64 extended limbs, window 0 = least significant) to out_windows (host). */
+int dalek_b200_edwards_msm_partial(dalek_b200_ctx *ctx, const uint8_t *scalars, const void *points,
+                                   int point_fmt, size_t n_local, size_t n_total,
+                                   uint64_t *out_windows);
+int dalek_b200_edwards_msm_partial_dev(dalek_b200_ctx *ctx, const void *d_scalars, const void *d_points,
+                                       int point_fmt, size_t n_local, size_t n_total,
+                                       uint64_t *out_windows);
+/* Combine the gathered accumulators of `ranks` shards (rank-major: ranks x window_count x 20 u64)
+ * into the final point: per-window sum over ranks, then total = total * 2^w + window
+ * (pippenger.rs:159). */
+int dalek_b200_edwards_msm_combine(dalek_b200_ctx *ctx, const uint64_t *windows, int ranks,
+                                   size_t n_total, uint8_t out_compressed[32], uint64_t out_limbs[20]);
+
+/* -------- RistrettoPoint ----------------------------------------------------------------- */
+/* n independent RistrettoPoint::multiscalar_mul([a_i, b_i], [G, H]) (constant-time Straus,
+ * C/ristretto.rs:964-977 -> C/edwards.rs:970-995 -> straus.rs:103-144), each result compressed
+ * (RistrettoPoint::compress, C/ristretto.rs:500-533).  G, H: CompressedRistretto; a, b: n x 32 B.
+ * out: n x 32 B.  Returns DALEK_NONE if G or H does not decode (C/ristretto.rs:266-345). */
+int dalek_b200_ristretto_double_base_batch(dalek_b200_ctx *ctx, const uint8_t *a, const uint8_t *b,
+                                           const uint8_t G[32], const uint8_t H[32], size_t n,
+                                           uint8_t *out);
+/* RistrettoPoint::vartime_multiscalar_mul over compressed Ristretto points
+ * (C/ristretto.rs:980-994); result as CompressedRistretto. */
+int dalek_b200_ristretto_vartime_msm(dalek_b200_ctx *ctx, const uint8_t *scalars,
+                                     const uint8_t *points, size_t n, uint8_t out_compressed[32]);
+
+/* -------- ed25519 --------------------------------------------------------------------------- */
+/*
+ * ed25519_dalek::verify_batch (E/batch.rs:146-251).
+ *   msgs / msg_lens   n message pointers and lengths          (messages: &[&[u8]])
+ *   sigs              n x 64 B R || s                          (signatures: &[Signature])
+ *   pubkeys           n x 32 B compressed keys                 (verifying_keys: &[VerifyingKey])
+ * In Rust a VerifyingKey already holds its decompressed point (E/verifying.rs:65-71); here keys
+ * arrive as bytes and VerifyingKey::from_bytes (E/verifying.rs:167-175) runs inside the call: an
+ * undecodable key is ED25519_ERR_POINT_DECOMPRESSION.  Then, in the reference's order
+ * (E/batch.rs:208-250): non-canonical s -> ED25519_ERR_SCALAR_FORMAT; undecodable R or a
+ * non-identity result -> ED25519_ERR_VERIFY; else 0.  No cofactor multiplication.
+ * Coefficients z_i: for n <= verify_chunk the Merlin transcript is exactly the reference's; for
+ * larger n the batch is cut into consecutive chunks of verify_chunk signatures, each with its own
+ * transcript, and one combined equation is checked (DESIGN.md "transcript chunking").
+ */
+int ed25519_b200_verify_batch(dalek_b200_ctx *ctx, const uint8_t *const *msgs, const size_t *msg_lens,
+                              const uint8_t *sigs, const uint8_t *pubkeys, size_t n);
+/* Same with the messages laid out back to back: message i = msgs_flat[msg_offsets[i] ..
+ * msg_offsets[i+1]) (n+1 offsets).  Avoids the host-side gather of the pointer form. */
+int ed25519_b200_verify_batch_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat,
+                                   const uint64_t *msg_offsets, const uint8_t *sigs,
+                                   const uint8_t *pubkeys, size_t n);
+/* Device-resident variant of the flat form (all four buffers are device pointers). */
+int ed25519_b200_verify_batch_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat,
+                                       const void *d_msg_offsets, const void *d_sigs,
+                                       const void *d_pubkeys, size_t n, size_t msgs_bytes);
+/* Debug/parity aid: the 16-byte z_i coefficients drawn in the last verify_batch call. */
+int ed25519_b200_last_zs(dalek_b200_ctx *ctx, uint8_t *zs_out, size_t n);
+
+/* -------- input synthesis (benchmarks / tests): fixed-base multiples and RFC 8032 signing ---- */
+/* out[i] = scalars[i] * B as extended limbs (EdwardsPoint::mul_base, C/edwards.rs:918-928). */
+int dalek_b200_edwards_mul_base_batch(dalek_b200_ctx *ctx, const uint8_t *scalars, size_t n,
+                                      uint64_t *out_limbs /* n x 20 */, uint8_t *out_compressed /* n x 32, nullable */);
+/* Deterministic Ed25519 keygen + sign on the GPU: seeds n x 32 B -> pubkeys n x 32 B, sigs n x 64 B
+ * (E/signing.rs, hazmat.rs:40-99); message layout as in verify_batch_flat. */
+int ed25519_b200_sign_batch_flat(dalek_b200_ctx *ctx, const uint8_t *seeds, const uint8_t *msgs_flat,
+                                 const uint64_t *msg_offsets, size_t n, uint8_t *pubkeys_out,
+                                 uint8_t *sigs_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

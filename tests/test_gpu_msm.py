@@ -1,0 +1,143 @@
+"""GPU parity tests for the MSM path: the CUDA engine (through the C ABI) against the CPU oracle on
+the same seeded inputs, at sizes crossing every reference threshold, plus
+size-independent identities at larger n."""
+import ctypes as C
+import hashlib
+import random
+
+import pytest
+
+import pyref
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0xDA1EC00000000001
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import curve25519_dalek_b200 as pkg
+    e = pkg.Engine(0)
+    yield e
+    e.close()
+
+
+def gen_case(oracle, n, seed=SEED, special=True):
+    """SURVEY 8(d) config 1 generators: s_i, t_i from labelled SHA-512; P_i = t_i * B."""
+    B = oracle.basepoint()
+    scalars, points = [], []
+    for i in range(n):
+        s = pyref.labelled_scalar(b"dalek-b200/scalar", seed, i)
+        t = pyref.labelled_scalar(b"dalek-b200/point", seed, i)
+        scalars.append(s.to_bytes(32, "little"))
+        points.append(oracle.scalarmul(t.to_bytes(32, "little"), B))
+    if special and n >= 8:
+        # edge scalars (0, 1, l-1, 2^255-1) and edge points (identity, 8-torsion)
+        scalars[0] = (0).to_bytes(32, "little")
+        scalars[1] = (1).to_bytes(32, "little")
+        scalars[2] = (pyref.L - 1).to_bytes(32, "little")
+        scalars[3] = (2**255 - 1).to_bytes(32, "little")
+        points[4] = oracle.identity()
+        points[5] = oracle.decompress((0).to_bytes(32, "little"))        # order-4 point (x, 0)
+        points[6] = oracle.decompress((pyref.p - 1).to_bytes(32, "little"))  # (0, -1), order 2
+    return scalars, points
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 100, 189, 190, 250, 256, 499, 500, 799, 800, 1000])
+def test_msm_parity_compressed_and_extended(eng, oracle, n):
+    scalars, points = gen_case(oracle, n)
+    want = oracle.compress(oracle.msm("optional", scalars, points)) if n else oracle.compress(oracle.identity())
+    sb = b"".join(scalars)
+    comp = b"".join(oracle.compress(p) for p in points)
+    rc, got, limbs = eng.edwards_vartime_msm(sb, comp, n, point_fmt=0, want_limbs=True)
+    assert rc == 0 and got == want
+    # returned limbs describe the same point (projective equality, C/edwards.rs:501-512)
+    assert oracle.compress(oracle.p3_from_limbs(limbs)) == want
+    # extended-limb input (the reference's in-memory EdwardsPoint, Z != 1)
+    ext = (C.c_uint64 * (20 * max(n, 1)))()
+    for i, p in enumerate(points):
+        q = oracle.add(oracle.double(p), p)            # 3p with non-trivial Z ...
+        q = oracle.sub(q, oracle.double(p))            # ... back to p, Z != 1
+        for k, v in enumerate(oracle.p3_limbs(q)):
+            ext[20 * i + k] = v
+    rc, got2, _ = eng.edwards_vartime_msm(sb, ext, n, point_fmt=1)
+    assert rc == 0 and got2 == want
+
+
+def test_msm_reference_kats(eng, oracle, kat):
+    """multiscalar_mul_vs_ed25519py (C/edwards.rs:2428-2435) through the engine."""
+    H = bytes.fromhex
+    a, b = H(kat["edwards"]["A_SCALAR"]["hex"]), H(kat["edwards"]["B_SCALAR"]["hex"])
+    A = H(kat["edwards"]["A_TIMES_BASEPOINT"]["hex"])
+    Bc = H(kat["constants"]["ED25519_BASEPOINT_COMPRESSED"]["hex"])
+    rc, got, _ = eng.edwards_vartime_msm(a + b, A + Bc, 2)
+    assert rc == 0 and got == H(kat["edwards"]["DOUBLE_SCALAR_MULT_RESULT"]["hex"])
+    rc, got, _ = eng.edwards_vartime_msm(a, Bc, 1)
+    assert rc == 0 and got == A
+
+
+def test_msm_none_on_bad_point(eng, oracle):
+    scalars, points = gen_case(oracle, 20, special=False)
+    comp = [oracle.compress(p) for p in points]
+    comp[7] = (2).to_bytes(32, "little")              # y = 2 is not on the curve
+    rc, _, _ = eng.edwards_vartime_msm(b"".join(scalars), b"".join(comp), 20)
+    assert rc == 1                                     # Option::None
+
+
+@pytest.mark.parametrize("bits", [4, 7, 8, 11, 13, 16])
+def test_msm_every_window_width(eng, oracle, bits):
+    scalars, points = gen_case(oracle, 300, seed=bits)
+    want = oracle.compress(oracle.msm("optional", scalars, points))
+    eng.set_option("window_bits", bits)
+    try:
+        rc, got, _ = eng.edwards_vartime_msm(b"".join(scalars), b"".join(oracle.compress(p) for p in points), 300)
+    finally:
+        eng.set_option("window_bits", 0)
+    assert rc == 0 and got == want
+
+
+def test_msm_skewed_buckets(eng, oracle):
+    """All scalars equal: every point lands in the same bucket of each window."""
+    scalars, points = gen_case(oracle, 700, special=False)
+    s = scalars[0]
+    want = oracle.compress(oracle.msm("optional", [s] * 700, points))
+    rc, got, _ = eng.edwards_vartime_msm(s * 700, b"".join(oracle.compress(p) for p in points), 700)
+    assert rc == 0 and got == want
+
+
+def test_msm_sharded_partial_combine(eng, oracle):
+    """contiguous shards -> window accumulators -> combine == single MSM."""
+    n, ranks = 1200, 4
+    scalars, points = gen_case(oracle, n)
+    comp = [oracle.compress(p) for p in points]
+    want = oracle.compress(oracle.msm("optional", scalars, points))
+    nwin = eng.msm_window_count(n)
+    allw = (C.c_uint64 * (20 * nwin * ranks))()
+    per = n // ranks
+    for r in range(ranks):
+        lo, hi = r * per, (r + 1) * per if r < ranks - 1 else n
+        rc, w = eng.edwards_msm_partial(b"".join(scalars[lo:hi]), b"".join(comp[lo:hi]), hi - lo, n)
+        assert rc == 0
+        for k in range(20 * nwin):
+            allw[r * 20 * nwin + k] = w[k]
+    got, _ = eng.edwards_msm_combine(allw, ranks, n)
+    assert got == want
+
+
+def test_msm_large_algebraic_identity(eng, oracle):
+    """C/edwards.rs:2281-2295 at n = 2^16: sum s_i (t_i B) == (sum s_i t_i) B, RHS by the oracle."""
+    import numpy as np
+    n = 1 << 16
+    rnd = random.Random(1234)
+    B = oracle.basepoint()
+    # points: t_i * B for a small pool extended by cheap additions so the oracle cost stays low
+    pool_t = [rnd.randrange(pyref.L) for _ in range(64)]
+    pool_p = [oracle.compress(oracle.scalarmul(t.to_bytes(32, "little"), B)) for t in pool_t]
+    idx = [rnd.randrange(64) for _ in range(n)]
+    ss = [rnd.randrange(pyref.L) for _ in range(n)]
+    k = sum(s * pool_t[j] for s, j in zip(ss, idx)) % pyref.L
+    want = oracle.compress(oracle.scalarmul(k.to_bytes(32, "little"), B))
+    sb = b"".join(s.to_bytes(32, "little") for s in ss)
+    pb = b"".join(pool_p[j] for j in idx)
+    rc, got, _ = eng.edwards_vartime_msm(sb, pb, n)
+    assert rc == 0 and got == want

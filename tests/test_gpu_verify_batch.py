@@ -1,0 +1,132 @@
+"""GPU parity tests for ed25519 verify_batch: verdicts and z_i coefficients of the CUDA engine
+against the CPU oracle (E/batch.rs:146-251), negative controls, chunked transcripts, fixtures."""
+import json
+import os
+import random
+
+import pytest
+
+import pyref
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OK, VERIFY, ARRAYLEN, SCALARFMT, POINTDEC = 0, 1, 2, 3, 4
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import curve25519_dalek_b200 as pkg
+    e = pkg.Engine(0)
+    yield e
+    e.close()
+
+
+def make_batch(oracle, n, seed=0, msg_len=None):
+    rnd = random.Random(seed)
+    msgs, sigs, pks = [], [], []
+    for _ in range(n):
+        sk = rnd.randbytes(32)
+        m = rnd.randbytes(msg_len if msg_len is not None else rnd.randrange(0, 300))
+        msgs.append(m); pks.append(oracle.public_key(sk)); sigs.append(oracle.sign(m, sk))
+    return msgs, sigs, pks
+
+
+def run(eng, msgs, sigs, pks):
+    return eng.verify_batch_raw(msgs, b"".join(sigs), b"".join(pks))
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 7, 64, 95, 96, 128, 129, 300])
+def test_verify_batch_valid_and_zs(eng, oracle, n):
+    msgs, sigs, pks = make_batch(oracle, n, seed=n)
+    chunk = 128
+    rc_o, zs_o = oracle.verify_batch(msgs, sigs, pks, chunk=chunk, want_zs=True)
+    assert rc_o == OK
+    assert run(eng, msgs, sigs, pks) == OK
+    assert eng.last_zs(n) == zs_o            # transcript parity (per chunk of 128)
+    if 0 < n <= chunk:                        # single chunk: exactly the reference's transcript
+        rc_o, zs_ref = oracle.verify_batch(msgs, sigs, pks, want_zs=True)
+        assert zs_ref == zs_o
+
+
+def test_verify_batch_chunk_option(eng, oracle):
+    msgs, sigs, pks = make_batch(oracle, 50, seed=77, msg_len=59)
+    for chunk in (1, 3, 16, 50, 4096):
+        eng.set_option("verify_chunk", chunk)
+        try:
+            assert run(eng, msgs, sigs, pks) == OK
+            rc, zs = oracle.verify_batch(msgs, sigs, pks, chunk=chunk, want_zs=True)
+            assert eng.last_zs(50) == zs
+        finally:
+            eng.set_option("verify_chunk", 128)
+
+
+def test_verify_batch_negative_controls(eng, oracle):
+    msgs, sigs, pks = make_batch(oracle, 33, seed=99, msg_len=59)
+    cases = []
+    bad = list(sigs); b = bytearray(bad[4]); b[33] ^= 1; bad[4] = bytes(b)
+    cases.append((msgs, bad, pks))                                   # bit flip in s
+    bad = list(sigs); b = bytearray(bad[9]); b[3] ^= 0x10; bad[9] = bytes(b)
+    cases.append((msgs, bad, pks))                                   # bit flip in R
+    bm = list(msgs); bm[2] = bytes([bm[2][0] ^ 1]) + bm[2][1:]
+    cases.append((bm, sigs, pks))                                    # bit flip in a message
+    bad = list(sigs); bad[0] = (2).to_bytes(32, "little") + bad[0][32:]
+    cases.append((msgs, bad, pks))                                   # R not on the curve
+    s = int.from_bytes(sigs[1][32:], "little") + pyref.L
+    bad = list(sigs); bad[1] = sigs[1][:32] + s.to_bytes(32, "little")
+    cases.append((msgs, bad, pks))                                   # non-canonical s
+    bk = list(pks); bk[3] = (2).to_bytes(32, "little")
+    cases.append((msgs, sigs, bk))                                   # undecodable key
+    sw = list(sigs); sw[0], sw[1] = sw[1], sw[0]
+    cases.append((msgs, sw, pks))                                    # swapped signatures
+    both = list(sigs); both[1] = sigs[1][:32] + s.to_bytes(32, "little"); both[0] = (2).to_bytes(32, "little") + both[0][32:]
+    cases.append((msgs, both, pks))                                  # bad R and bad s: ScalarFormat wins
+    want = [VERIFY, VERIFY, VERIFY, VERIFY, SCALARFMT, POINTDEC, VERIFY, SCALARFMT]
+    for (m, s_, k), w in zip(cases, want):
+        assert oracle.verify_batch(m, s_, k) == w
+        assert run(eng, m, s_, k) == w
+
+
+def test_verify_batch_reference_fixtures(eng, oracle):
+    """TESTVECTORS (valid signatures) verify as one batch; every VALIDATIONVECTORS case gets the
+    same verdict from the engine as from the oracle's verify_batch on that single signature."""
+    with open(os.path.join(ROOT, "tests", "golden", "ed25519_testvectors.json")) as f:
+        tv = json.load(f)["vectors"]
+    H = bytes.fromhex
+    msgs, sigs, pks = [H(v["msg"]) for v in tv], [H(v["sig"]) for v in tv], [H(v["pk"]) for v in tv]
+    assert run(eng, msgs, sigs, pks) == OK
+    with open(os.path.join(ROOT, "tests", "golden", "ed25519_validation.json")) as f:
+        vv = json.load(f)["vectors"]
+    for v in vv[::7]:
+        m, s_, k = [v["msg"].encode()], [H(v["sig"])], [H(v["key"])]
+        assert run(eng, m, s_, k) == oracle.verify_batch(m, s_, k), v["number"]
+
+
+def test_verify_batch_python_api(eng, oracle):
+    import curve25519_dalek_b200 as pkg
+    msgs, sigs, pks = make_batch(oracle, 12, seed=5)
+    assert pkg.verify_batch(msgs, sigs, pks, engine=eng) is None
+    with pytest.raises(pkg.SignatureError) as ei:
+        pkg.verify_batch(msgs, sigs[:-1], pks, engine=eng)
+    assert ei.value.kind == "ArrayLength"
+    bad = list(sigs); b = bytearray(bad[4]); b[40] ^= 1; bad[4] = bytes(b)
+    with pytest.raises(pkg.SignatureError) as ei:
+        pkg.verify_batch(msgs, bad, pks, engine=eng)
+    assert ei.value.kind == "Verify"
+
+
+def test_verify_batch_flat_large(eng, oracle):
+    """n = 20000 with 64 distinct keys: all valid -> Ok; one corrupted message -> Verify."""
+    import numpy as np
+    n, nk = 20000, 64
+    rnd = random.Random(4242)
+    seeds = [rnd.randbytes(32) for _ in range(nk)]
+    keys = [oracle.public_key(s) for s in seeds]
+    msgs = [(b"a" * 51) + i.to_bytes(8, "little") for i in range(n)]
+    sigs = [oracle.sign(msgs[i], seeds[i % nk]) for i in range(n)]
+    flat = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy()
+    offs = np.arange(n + 1, dtype=np.uint64) * 59
+    sg = np.frombuffer(b"".join(sigs), dtype=np.uint8).copy()
+    pk = np.frombuffer(b"".join(keys[i % nk] for i in range(n)), dtype=np.uint8).copy()
+    assert eng.verify_batch_flat(flat, offs, sg, pk, n) == OK
+    flat[59 * 12345 + 7] ^= 1
+    assert eng.verify_batch_flat(flat, offs, sg, pk, n) == VERIFY
