@@ -1,0 +1,556 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200 MSM / batch-verify engine.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload msm|verify] [--impl reference]
+
+Metric (BASELINE.json): Pippenger MSM points/sec (default workload) and Ed25519 verify_batch
+signatures/sec (reported in the same line under "verify_batch", or as the main metric with
+--workload verify).  One "step" = one pass of the hot path over one batch of synthetic input.
+
+  N = 1 : BASELINE configs[1] -- one MSM over 2^20 (scalar, EdwardsPoint) pairs, 192 B per pair
+          (32 B scalar + 160 B radix-2^51 extended point), inputs resident in HBM when timing starts.
+  N > 1 : BASELINE configs[3] layout -- 2^21 pairs per GPU (2^24 at N = 8), contiguous shards, each
+          rank reduces its shard to window accumulators, one NCCL all-gather of the accumulators,
+          every rank combines.  Weak scaling.
+
+`value` is device-resident throughput; `e2e` is the same call made through the C ABI with HOST
+buffers (pinned), host->device copies and the result read-back inside the timed region.
+`--impl reference` times the CPU oracle (the Rust reference cannot be built in this image) on all
+host cores with the same metric.  Only the cpu_baseline / reference legs touch oracle/.
+"""
+import argparse
+import ctypes as C
+import hashlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+L_ORDER = 2**252 + 27742317777372353535851937790883648493
+SEED = 0xDA1EC00000000001
+IMAD_WIDE_PEAK_PER_S = 8.96e12      # measured on this pool's B200, profiles/microbench_r1.json
+
+
+# ------------------------------------------------------------------------------------------ utils
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def labelled_scalars(label, n, seed=SEED):
+    """n x 32 B: from_bytes_mod_order_wide(SHA-512(label || seed || i)) (SURVEY 8d generators).  Uses
+    SHAKE-free bulk hashing through hashlib; 2^21 scalars take ~2 s."""
+    import numpy as np
+    out = np.empty((n, 32), dtype=np.uint8)
+    pre = label + seed.to_bytes(8, "little")
+    for i in range(n):
+        h = hashlib.sha512(pre + i.to_bytes(8, "little")).digest()
+        out[i] = np.frombuffer((int.from_bytes(h, "little") % L_ORDER).to_bytes(32, "little"), dtype=np.uint8)
+    return out
+
+
+def fast_scalars(n, seed):
+    """Cheaper bulk generator for 2^20+ scalars: numpy PCG64 bytes reduced below 2^252 (uniform 252-bit
+    values, all < l).  Used for the timed workloads; the labelled generator is used in the parity tests."""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    a[:, 31] &= 0x0F
+    return a
+
+
+# ------------------------------------------------------------------------------------------ MSM workload
+class MsmWorkload:
+    def __init__(self, eng, n_local, n_total, rank, torch):
+        import numpy as np
+        self.eng, self.n, self.n_total, self.torch = eng, n_local, n_total, torch
+        self.np = np
+        # points P_i = t_i * B generated on the GPU (fixed-base kernel), extended limbs (Z != 1 is
+        # produced by the additions inside the kernel); scalars uniform 252-bit.
+        self.t = fast_scalars(n_local, seed=1000 + rank)
+        self.s = fast_scalars(n_local, seed=2000 + rank)
+        limbs, _ = eng.mul_base_batch(self.t, n_local, want_compressed=False)
+        pts = np.frombuffer(limbs, dtype=np.uint64).reshape(n_local, 20).copy()
+        self.h_scalars = torch.from_numpy(self.s).pin_memory()
+        self.h_points = torch.from_numpy(pts.view(np.int64)).pin_memory()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.d_scalars = self.h_scalars.to(dev)
+        self.d_points = self.h_points.to(dev)
+        torch.cuda.synchronize()
+        self.bytes_per_step = n_local * 192
+
+    def expected_local_scalar(self):
+        """sum s_i t_i mod l (C/edwards.rs:2281-2295 identity), vectorised big-int arithmetic."""
+        s = [int.from_bytes(r.tobytes(), "little") for r in self.s]
+        t = [int.from_bytes(r.tobytes(), "little") for r in self.t]
+        return sum(a * b for a, b in zip(s, t)) % L_ORDER
+
+    def step_device_single(self):
+        rc, comp, _ = self.eng.edwards_vartime_msm(self.d_scalars.data_ptr(), self.d_points.data_ptr(), self.n,
+                                                   point_fmt=1, device_ptrs=True)
+        assert rc == 0
+        return comp
+
+    def step_host_single(self):
+        rc, comp, _ = self.eng.edwards_vartime_msm(self.h_scalars.data_ptr(), self.h_points.data_ptr(), self.n,
+                                                   point_fmt=1, device_ptrs=False)
+        assert rc == 0
+        return comp
+
+    def step_partial(self, host):
+        s = self.h_scalars if host else self.d_scalars
+        p = self.h_points if host else self.d_points
+        rc, win = self.eng.edwards_msm_partial(s.data_ptr(), p.data_ptr(), self.n, self.n_total, point_fmt=1,
+                                               device_ptrs=not host)
+        assert rc == 0
+        return win
+
+
+def run_msm(args, rank, world, local):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import curve25519_dalek_b200 as pkg
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = pkg.Engine(local)
+    n_local = args.pairs_per_gpu or ((1 << 20) if world == 1 else (1 << 21))
+    n_total = n_local * world
+    wl = MsmWorkload(eng, n_local, n_total, rank, torch)
+    nwin = eng.msm_window_count(n_total)
+    dev = torch.device("cuda", local)
+
+    def step(host=False):
+        if world == 1:
+            return wl.step_host_single() if host else wl.step_device_single()
+        win = wl.step_partial(host)
+        mine = torch.frombuffer(bytearray(bytes(win)), dtype=torch.int64).to(dev)
+        gathered = torch.empty(world * nwin * 20, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, mine)          # the one exchange step of the sharded MSM
+        allw = gathered.cpu().numpy().view(np.uint64)
+        comp, _ = eng.edwards_msm_combine(allw, world, n_total)
+        return comp
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # --- correctness at full size: sum s_i (t_i B) == (sum s_i t_i mod l) B  (C/edwards.rs:2281-2295)
+    got = step()
+    k_local = wl.expected_local_scalar()
+    if world > 1:
+        ks = [None] * world
+        dist.all_gather_object(ks, k_local)
+        k = sum(ks) % L_ORDER
+    else:
+        k = k_local
+    _, want = eng.mul_base_batch(np.frombuffer(k.to_bytes(32, "little"), dtype=np.uint8).copy(), 1)
+    parity = (got == want)
+    if not parity:
+        raise SystemExit("bench: MSM result does not satisfy the algebraic identity")
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    kernel_ms = []
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        kernel_ms.append(eng.last_kernel_ms()[0])
+    barrier()
+    t1 = time.perf_counter()
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    elapsed = float(elapsed.item())
+
+    # --- end to end: host (pinned) buffers through the same C-ABI call
+    for _ in range(min(2, args.warmup)):
+        step(host=True)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(host=True)
+    barrier()
+    e1 = time.perf_counter()
+    e2e_t = torch.tensor([e1 - e0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_t = float(e2e_t.item())
+
+    line = None
+    if rank == 0:
+        peaks, how = measured_peaks()
+        kms = statistics.mean(kernel_ms)
+        algo_bytes = n_local * 192
+        achieved = algo_bytes / (kms * 1e-3) / 1e9
+        c = eng_window_bits(n_total)
+        adds = n_local * ((253 + c - 1) // c)
+        imad_wide = adds * 8 * 100           # 8M per projective-Niels add, 100 IMAD.WIDE per field mul
+        line = {
+            "metric": "Pippenger MSM points/sec", "value": n_total * args.steps / elapsed, "unit": "points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (radix 2^25.5), exact",
+            "data": "synthetic: uniform 252-bit scalars, points t_i*B from the on-GPU fixed-base kernel",
+            "config": {"workload": "pippenger_msm", "pairs_total": n_total, "pairs_per_gpu": n_local,
+                       "point_format": "extended radix-2^51 limbs (160 B)", "window_bits": c,
+                       "l2": "inputs (%.0f MB per GPU) exceed the 126 MB L2" % (algo_bytes / 1e6),
+                       "timing": "wall clock around K blocking C-ABI calls, bracketed by barrier + device sync, max over ranks",
+                       "parity": "algebraic identity sum s_i(t_i B) == (sum s_i t_i)B checked at full size"},
+            "e2e": {"value": n_total * args.steps / e2e_t, "unit": "points/s",
+                    "h2d_bytes_per_step": n_local * 192, "d2h_bytes_per_step": 192 if world == 1 else nwin * 160 + 192},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_bucket_accumulate", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)", "kernel_ms": kms,
+                         "note": "integer-multiply bound, see roofline_imad"},
+            "roofline_imad": {"bound": "IMAD.WIDE.U32 issue", "achieved": imad_wide / (kms * 1e-3) / 1e12,
+                              "peak": IMAD_WIDE_PEAK_PER_S / 1e12, "unit": "T IMAD.WIDE/s",
+                              "frac": imad_wide / (kms * 1e-3) / IMAD_WIDE_PEAK_PER_S,
+                              "peak_source": "measured microbenchmark, profiles/microbench_r1.json",
+                              "algorithmic_ops_per_launch": imad_wide},
+            "clocks": clocks,
+        }
+    return line, eng, (rank, world, local)
+
+
+def eng_window_bits(n):
+    best, best_cost = 4, 1e300
+    for c in range(4, 21):
+        W = (253 + c - 1) // c
+        cost = W * (n + 2.6 * (1 << (c - 1)))
+        if cost < best_cost:
+            best, best_cost = c, cost
+    return best
+
+
+# ------------------------------------------------------------------------------------------ verify workload
+def build_verify_inputs(eng, n, nkeys=1024):
+    """BASELINE configs[2]: n signatures over 59-byte messages (51 x 'a' || i_le64) by `nkeys` keys,
+    signed on the GPU (byte-identical to RFC 8032 signing, spot-checked in tests)."""
+    import numpy as np
+    seeds_k = np.stack([np.frombuffer(hashlib.sha512(b"dalek-b200/sk" + SEED.to_bytes(8, "little") + k.to_bytes(8, "little")).digest()[:32], dtype=np.uint8)
+                        for k in range(nkeys)])
+    idx = np.arange(n) % nkeys
+    seeds = np.ascontiguousarray(seeds_k[idx])
+    msgs = np.full((n, 59), ord("a"), dtype=np.uint8)
+    msgs[:, 51:] = np.arange(n, dtype="<u8").view(np.uint8).reshape(n, 8)
+    flat = np.ascontiguousarray(msgs.reshape(-1))
+    offs = (np.arange(n + 1, dtype=np.uint64) * 59)
+    pks, sigs = eng.sign_batch_flat(seeds, flat, offs, n)
+    return flat, offs, np.frombuffer(sigs, dtype=np.uint8).copy(), np.frombuffer(pks, dtype=np.uint8).copy()
+
+
+def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import curve25519_dalek_b200 as pkg
+    steps = steps or args.steps
+    warmup = args.warmup if warmup is None else warmup
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = eng or pkg.Engine(local)
+    n = args.sigs_per_gpu or (1 << 22)
+    flat, offs, sigs, pks = build_verify_inputs(eng, n)
+    dev = torch.device("cuda", local)
+    h = [torch.from_numpy(x if x.dtype == np.uint8 else x.view(np.int64)).pin_memory() for x in (flat, offs, sigs, pks)]
+    d = [x.to(dev) for x in h]
+    torch.cuda.synchronize()
+
+    def step(host=False):
+        b = h if host else d
+        rc = eng.verify_batch_flat(b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(), n,
+                                   device_ptrs=not host, msgs_bytes=n * 59)
+        if rc != 0:
+            raise SystemExit("bench: verify_batch returned %d on valid signatures" % rc)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # negative control: one flipped message bit must give Verify (1)
+    d[0][59 * 777 + 3] ^= 1
+    rc = eng.verify_batch_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, device_ptrs=True)
+    d[0][59 * 777 + 3] ^= 1
+    if rc != 1:
+        raise SystemExit("bench: corrupted batch was not rejected (rc=%d)" % rc)
+    for _ in range(warmup):
+        step()
+    sampler = ClockSampler(local)
+    kernel_ms = []
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+        kernel_ms.append(eng.last_kernel_ms()[0])
+    barrier()
+    t1 = time.perf_counter()
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    el = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    el = float(el.item())
+    step(host=True)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(steps):
+        step(host=True)
+    barrier()
+    e1 = time.perf_counter()
+    et = torch.tensor([e1 - e0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    et = float(et.item())
+    if rank != 0:
+        return None
+    peaks, how = measured_peaks()
+    kms = statistics.mean(kernel_ms)
+    achieved = n * 155 / (el / steps) / 1e9
+    return {
+        "metric": "Ed25519 verify_batch signatures/sec", "value": n * world * steps / el, "unit": "sigs/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": el / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (radix 2^25.5), exact", "data": "synthetic: 59-byte messages, 1024 keys, signatures made on the GPU (RFC 8032)",
+        "config": {"workload": "ed25519_verify_batch", "signatures_per_gpu": n, "message_bytes": 59, "distinct_keys": 1024,
+                   "verify_chunk": 128, "keys": "32-byte encodings, decompressed inside the call",
+                   "l2": "inputs (%.0f MB) exceed the 126 MB L2" % (n * 155 / 1e6),
+                   "replicas": "independent batches per GPU, no collective" if world > 1 else "single batch"},
+        "e2e": {"value": n * world * steps / et, "unit": "sigs/s", "h2d_bytes_per_step": n * 155 + (n + 1) * 8, "d2h_bytes_per_step": 192},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "whole call (155 B per signature)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": how,
+                     "bucket_kernel_ms": kms, "note": "integer-multiply bound (decompression + MSM)"},
+        "clocks": clocks,
+    }
+
+
+# ------------------------------------------------------------------------------------------ CPU baseline (oracle)
+def cpu_msm_baseline(n, threads):
+    """Oracle Pippenger (reference algorithm, w = 8) on `n` pairs split over `threads` host threads."""
+    import numpy as np
+    import oracle_lib
+    orc = oracle_lib.load()
+    lib = orc.lib
+    pts = np.empty((n, 20), dtype=np.uint64)
+    t0b = (0x1234567 + SEED).to_bytes(32, "little")
+    qb = (0x9e3779b97f4a7c15f39cc0605cedc834 % L_ORDER).to_bytes(32, "little")
+    lib.oracle_points_progression(pts.ctypes.data_as(C.c_void_p), C.c_size_t(n), t0b, qb)
+    sc = fast_scalars(n, seed=77)
+    outs = np.zeros((threads, 20), dtype=np.uint64)
+    bounds = [n * i // threads for i in range(threads + 1)]
+
+    def work(i):
+        lo, hi = bounds[i], bounds[i + 1]
+        lib.oracle_msm_limbs(outs[i].ctypes.data_as(C.c_void_p), sc[lo:hi].ctypes.data_as(C.c_void_p),
+                             pts[lo:hi].ctypes.data_as(C.c_void_p), C.c_size_t(hi - lo))
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    res = (C.c_uint8 * 32)()
+    lib.oracle_sum_points(res, None, outs.ctypes.data_as(C.c_void_p), C.c_size_t(threads))
+    dt = time.perf_counter() - t0
+    return n / dt, dt
+
+
+def cpu_verify_baseline(nsigs, threads, batch=256):
+    import oracle_lib
+    orc = oracle_lib.load()
+    msgs = [b"a" * 51 + i.to_bytes(8, "little") for i in range(batch)]
+    seeds = [hashlib.sha512(b"dalek-b200/sk" + k.to_bytes(8, "little")).digest()[:32] for k in range(batch)]
+    pks = [orc.public_key(s) for s in seeds]
+    sigs = [orc.sign(m, s) for m, s in zip(msgs, seeds)]
+    reps = max(1, nsigs // (batch * threads))
+    ok = []
+
+    def work():
+        for _ in range(reps):
+            ok.append(orc.verify_batch(msgs, sigs, pks))
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work) for _ in range(threads)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    dt = time.perf_counter() - t0
+    assert all(r == 0 for r in ok)
+    return reps * threads * batch / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    threads = os.cpu_count() or 1
+    steps = max(1, args.steps)
+    if args.workload == "verify":
+        vals = []
+        for _ in range(args.warmup and 1):
+            cpu_verify_baseline(256 * threads, threads)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            v, dt = cpu_verify_baseline(256 * threads * 4, threads)
+            vals.append(v)
+        el = time.perf_counter() - t0
+        val = statistics.mean(vals)
+        metric, unit, sample = "Ed25519 verify_batch signatures/sec", "sigs/s", "each step: %d threads x 4 batches of 256 signatures (reference's largest published batch size)" % threads
+        config = {"workload": "ed25519_verify_batch", "batch": 256}
+    else:
+        n = 1 << 17
+        vals = []
+        for _ in range(args.warmup and 1):
+            cpu_msm_baseline(1 << 14, threads)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            v, dt = cpu_msm_baseline(n, threads)
+            vals.append(v)
+        el = time.perf_counter() - t0
+        val = statistics.mean(vals)
+        metric, unit = "Pippenger MSM points/sec", "points/s"
+        sample = "each step: one 2^17-pair MSM (reference Pippenger, w=8) split into %d independent sub-MSMs, one per host thread, partial sums added" % threads
+        config = {"workload": "pippenger_msm", "pairs_total": n, "point_format": "extended radix-2^51 limbs (160 B)"}
+    return {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64 limbs (radix 2^51), exact", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": val, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU oracle = C restatement of the reference's serial u64 backend (Rust toolchain absent: oracle/_ref cannot be built)"}
+
+
+# ------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="msm", choices=["msm", "verify"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=0)
+    ap.add_argument("--sigs-per-gpu", type=int, default=0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary verify_batch / cpu_baseline legs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        line = run_reference(args, rank, world)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+    if world != args.gpus and rank == 0:
+        print("bench: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world), file=sys.stderr)
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench: no CUDA device; the engine has no CPU fallback")
+    if args.workload == "verify":
+        line = run_verify(args, rank, world, local)
+    else:
+        line, eng, _ = run_msm(args, rank, world, local)
+        if not args.no_extras and world == 1:
+            v = run_verify(args, rank, world, local, eng=eng, steps=min(args.steps, 5), warmup=3)
+            line["verify_batch"] = {k: v[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "config", "gpu_launches", "roofline")}
+    if rank == 0 and world == 1 and not args.no_extras:
+        threads = 1
+        if args.workload == "verify":
+            val, dt = cpu_verify_baseline(4096, 1)
+            line["cpu_baseline"] = {"value": val, "unit": "sigs/s", "cores": 1, "kind": "port",
+                                    "sample": "16 oracle verify_batch calls of 256 signatures, 1 thread (%.1f s)" % dt}
+        else:
+            val, dt = cpu_msm_baseline(1 << 19, threads)
+            line["cpu_baseline"] = {"value": val, "unit": "points/s", "cores": 1, "kind": "port",
+                                    "sample": "one 2^19-pair oracle Pippenger MSM (w=8), 1 thread (%.1f s)" % dt}
+            if "verify_batch" in line:
+                v2, dt2 = cpu_verify_baseline(4096, 1)
+                line["verify_batch"]["cpu_baseline"] = {"value": v2, "unit": "sigs/s", "cores": 1, "kind": "port",
+                                                        "sample": "16 oracle verify_batch calls of 256 signatures, 1 thread (%.1f s)" % dt2}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1 and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -2,7 +2,7 @@
 the C ABI of libdalek_b200.so (include/dalek_b200.h).
 
 The product path is the CUDA library; there is no CPU fallback.  Importing this package never
-touches oracle/.  Names follow the reference:
+touches the CPU checker used by the tests.  Names follow the reference:
   EdwardsPoint.vartime_multiscalar_mul / optional_multiscalar_mul / multiscalar_mul
       (curve25519-dalek/src/traits.rs:78-262, src/edwards.rs:966-1031)
   RistrettoPoint.multiscalar_mul / vartime_multiscalar_mul (src/ristretto.rs:964-994)

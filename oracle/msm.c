@@ -128,3 +128,41 @@ void edwards_vartime_double_scalar_mul_basepoint(ge_p3 *o, const uint8_t a[32], 
     pts[0] = *A; ge_basepoint(&pts[1]);
     msm_straus_vartime(o, sc, pts, NULL, 2);
 }
+
+/* ---- helpers for tests / bench input synthesis (not part of the reference) ---- */
+/* out[i] = (t0 + i*q) * B, by one scalar multiplication and repeated addition; the points carry
+ * non-trivial Z like the outputs of the reference's own arithmetic. */
+void oracle_points_progression(ge_p3 *out, size_t n, const uint8_t t0[32], const uint8_t q[32])
+{
+    ge_p3 B, Q, P;
+    ge_basepoint(&B);
+    ge_scalarmul(&P, t0, &B);
+    ge_scalarmul(&Q, q, &B);
+    for (size_t i = 0; i < n; i++) { out[i] = P; ge_p3_add(&P, &P, &Q); }
+}
+
+/* compress(sum scalars[i] * points[i]) with the reference's dispatch; points as n x 20 u64 limbs */
+int oracle_msm_compressed(uint8_t out[32], const uint8_t *scalars, const ge_p3 *points, size_t n)
+{
+    ge_p3 r;
+    if (!edwards_optional_multiscalar_mul(&r, scalars, points, NULL, n)) return 0;
+    ge_compress(out, &r);
+    return 1;
+}
+
+/* sum of already-computed points given as limbs (to combine per-thread partial MSMs) */
+void oracle_sum_points(uint8_t out[32], uint64_t out_limbs[20], const ge_p3 *points, size_t n)
+{
+    ge_p3 acc; ge_identity(&acc);
+    for (size_t i = 0; i < n; i++) ge_p3_add(&acc, &acc, &points[i]);
+    ge_compress(out, &acc);
+    if (out_limbs) ge_p3_to_limbs(out_limbs, &acc);
+}
+
+int oracle_msm_limbs(uint64_t out_limbs[20], const uint8_t *scalars, const ge_p3 *points, size_t n)
+{
+    ge_p3 r;
+    if (!edwards_optional_multiscalar_mul(&r, scalars, points, NULL, n)) return 0;
+    ge_p3_to_limbs(out_limbs, &r);
+    return 1;
+}

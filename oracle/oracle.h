@@ -136,6 +136,12 @@ void edwards_multiscalar_mul(ge_p3 *o, const uint8_t *scalars, const ge_p3 *poin
 void edwards_vartime_double_scalar_mul_basepoint(ge_p3 *o, const uint8_t a[32], const ge_p3 *A,
                                                  const uint8_t b[32]);
 
+/* helpers for tests / bench input synthesis (not reference functions) */
+void oracle_points_progression(ge_p3 *out, size_t n, const uint8_t t0[32], const uint8_t q[32]);
+int  oracle_msm_compressed(uint8_t out[32], const uint8_t *scalars, const ge_p3 *points, size_t n);
+int  oracle_msm_limbs(uint64_t out_limbs[20], const uint8_t *scalars, const ge_p3 *points, size_t n);
+void oracle_sum_points(uint8_t out[32], uint64_t out_limbs[20], const ge_p3 *points, size_t n);
+
 /* ---------------- ristretto: C/ristretto.rs -------------------------------- */
 int  ristretto_decompress(ge_p3 *o, const uint8_t s[32]);             /* ristretto.rs:266-345 */
 void ristretto_compress(uint8_t s[32], const ge_p3 *p);               /* ristretto.rs:500-533 */
