@@ -213,7 +213,7 @@ static int verify_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t
     if ((rc = ws_reserve(ctx, ctx->scalars, m * 32))) return rc;
     if ((rc = ws_reserve(ctx, ctx->points, m * sizeof(ge_niels_packed)))) return rc;
     if ((rc = ws_reserve(ctx, ctx->flags, 64))) return rc;
-    const uint32_t nsum = 4096;
+    const uint32_t nsum = 32768;
     if ((rc = ws_reserve(ctx, ctx->misc5, (size_t)nsum * 9 * 4))) return rc;
     int *flags = (int *)ctx->flags.p;
     uint32_t *scalars = (uint32_t *)ctx->scalars.p;

@@ -30,7 +30,7 @@ struct dalek_b200_ctx {
     int last_kernel_launches = 0;
     // device workspaces (grown on demand, reused across calls)
     DevBuf scalars, points_in, points, digits, counts, offsets, sorted, buckets, red_a, red_b, red_c,
-        red_d, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table;
+        red_d, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums;
     bool base_table_ready = false;
     // pinned host staging
     void *h_pinned = nullptr;

@@ -20,9 +20,12 @@
 // (window, scalar); sorted indices 4 B per entry; bucket sums 160 B (10 x u32 limbs x 4).
 #include <algorithm>
 #include <cstdio>
+#include <utility>
+#include <vector>
 
 #include "../../include/dalek_b200.h"
 #include "engine.h"
+#include "warp4.cuh"
 
 // ------------------------------------------------------------------------------------------
 static inline unsigned cdiv(size_t a, unsigned b) { return (unsigned)((a + b - 1) / b); }
@@ -146,26 +149,59 @@ __global__ void k_digits(const uint4 *__restrict__ scalars, size_t n, int c, int
     }
 }
 
-// one CTA per window: exclusive scan of counts -> offsets (relative to the window's segment)
-__global__ void k_scan_window(const uint32_t *__restrict__ counts, uint32_t *__restrict__ offsets, uint32_t nbuckets)
+// per-window exclusive scan of counts -> offsets (relative to the window's segment), multi-block:
+// k_scan_partial (sum of each 4096-entry part), k_scan_bases (exclusive scan of the part sums of a
+// window, one CTA per window), k_scan_apply (local scan + part base).
+#define SCAN_PART 4096u
+__global__ void __launch_bounds__(1024) k_scan_partial(const uint32_t *__restrict__ in, uint32_t nbuckets, uint32_t parts,
+                                                       uint32_t *__restrict__ part_sums)
 {
-    __shared__ uint32_t sh[1024];
-    const uint32_t *cin = counts + (size_t)blockIdx.x * nbuckets;
-    uint32_t *out = offsets + (size_t)blockIdx.x * nbuckets;
-    uint32_t per = (nbuckets + blockDim.x - 1) / blockDim.x;
-    uint32_t lo = threadIdx.x * per, hi = min(lo + per, nbuckets);
-    uint32_t sum = 0;
-    for (uint32_t k = lo; k < hi; k++) sum += cin[k];
-    sh[threadIdx.x] = sum;
+    __shared__ uint32_t sh[32];
+    uint32_t w = blockIdx.x / parts, part = blockIdx.x % parts;
+    const uint32_t *src = in + (size_t)w * nbuckets;
+    uint32_t base = part * SCAN_PART + threadIdx.x * 4, sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (base + k < nbuckets) sum += src[base + k];
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sum;
     __syncthreads();
-    for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
-        uint32_t v = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
-        __syncthreads();
-        sh[threadIdx.x] += v;
-        __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t v = sh[threadIdx.x];
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+        if (threadIdx.x == 0) part_sums[blockIdx.x] = v;
     }
-    uint32_t run = sh[threadIdx.x] - sum;
-    for (uint32_t k = lo; k < hi; k++) { out[k] = run; run += cin[k]; }
+}
+__global__ void k_scan_bases(uint32_t *__restrict__ part_sums, uint32_t parts)
+{
+    // one CTA (one thread is enough: parts <= 128) per window: in-place exclusive scan
+    if (threadIdx.x) return;
+    uint32_t *p = part_sums + (size_t)blockIdx.x * parts, run = 0;
+    for (uint32_t k = 0; k < parts; k++) { uint32_t v = p[k]; p[k] = run; run += v; }
+}
+__global__ void __launch_bounds__(1024) k_scan_apply(const uint32_t *__restrict__ in, const uint32_t *__restrict__ part_base,
+                                                     uint32_t nbuckets, uint32_t parts, uint32_t *__restrict__ out)
+{
+    __shared__ uint32_t sh[32];
+    uint32_t w = blockIdx.x / parts, part = blockIdx.x % parts;
+    const uint32_t *src = in + (size_t)w * nbuckets;
+    uint32_t *dst = out + (size_t)w * nbuckets;
+    uint32_t base = part * SCAN_PART + threadIdx.x * 4;
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = base + k < nbuckets ? src[base + k] : 0; sum += v[k]; }
+    uint32_t incl = sum;                                   // inclusive scan of thread sums inside the warp
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((threadIdx.x & 31) >= d) incl += t; }
+    if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t x = sh[threadIdx.x], inc2 = x;
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc2, d); if (threadIdx.x >= d) inc2 += t; }
+        sh[threadIdx.x] = inc2 - x;                        // exclusive warp bases
+    }
+    __syncthreads();
+    uint32_t run = part_base[blockIdx.x] + sh[threadIdx.x >> 5] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (base + k < nbuckets) dst[base + k] = run; run += v[k]; }
 }
 
 __global__ void k_scatter(const uint64_t *__restrict__ entries, const uint32_t *__restrict__ offsets, size_t n,
@@ -184,20 +220,95 @@ __global__ void k_scatter(const uint64_t *__restrict__ entries, const uint32_t *
 }
 
 // ------------------------------------------------------------------------------------------
-// bucket accumulation: one thread per (window, bucket)
-template <int KIND>
-__global__ void __launch_bounds__(128)
-k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict__ sorted,
-                    const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets, size_t n,
-                    uint32_t nbuckets, uint32_t total_buckets, ge_p3_raw *__restrict__ buckets)
+// Bucket accumulation as a list of tasks.  A task is at most TASK_LEN consecutive entries of one
+// bucket; a bucket with more entries (skewed inputs: the 128-bit z_i of verify_batch put n/256
+// points into each of 256 buckets of one window; adversarial inputs can put everything into one)
+// is cut into several tasks whose partial sums are added afterwards by k_heavy_fixup.  Inside a
+// CTA the 128 tasks are sorted by length so that the lanes of a warp run the same trip count.
+#define TASK_LEN 64u
+
+// also appends every bucket that needs more than one task to the heavy list (heavy[0] = count)
+__global__ void k_task_count(const uint32_t *__restrict__ counts, uint32_t total_buckets, uint32_t *__restrict__ ntasks,
+                             uint32_t *__restrict__ heavy)
+{
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_buckets) return;
+    uint32_t c = counts[t];
+    uint32_t k = c <= TASK_LEN ? 1u : (c + TASK_LEN - 1) / TASK_LEN;
+    ntasks[t] = k;
+    if (k > 1) heavy[1 + atomicAdd(&heavy[0], 1u)] = t;
+}
+
+// per-window bases of the task lists (exclusive prefix over windows) and the grand total
+__global__ void k_task_bases(const uint32_t *__restrict__ ntasks, const uint32_t *__restrict__ task_off, uint32_t nbuckets,
+                             int nwin, uint32_t *__restrict__ win_base /* nwin + 1 */)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t run = 0;
+    for (int w = 0; w < nwin; w++) {
+        win_base[w] = run;
+        size_t last = (size_t)w * nbuckets + nbuckets - 1;
+        run += task_off[last] + ntasks[last];
+    }
+    win_base[nwin] = run;
+}
+
+// task p = (bucket t, piece j) stored as two u32
+__global__ void k_task_fill(const uint32_t *__restrict__ ntasks, const uint32_t *__restrict__ task_off,
+                            const uint32_t *__restrict__ win_base, uint32_t nbuckets, uint32_t total_buckets,
+                            uint2 *__restrict__ tasks)
 {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_buckets) return;
     uint32_t w = t / nbuckets;
-    uint32_t cnt = counts[t];
-    const uint32_t *idx = sorted + (size_t)w * n + offsets[t];
+    uint32_t base = win_base[w] + task_off[t], k = ntasks[t];
+    for (uint32_t j = 0; j < k; j++) tasks[base + j] = make_uint2(t, j);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128, 4)
+k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict__ sorted,
+                    const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets,
+                    const uint32_t *__restrict__ ntasks, const uint2 *__restrict__ tasks,
+                    const uint32_t *__restrict__ win_base, int nwin, size_t n, uint32_t nbuckets,
+                    ge_p3_raw *__restrict__ buckets, ge_p3_raw *__restrict__ task_sums)
+{
+    __shared__ uint32_t s_key[128];     // (len << 8) | local task index, sorted descending
+    const uint32_t total_tasks = win_base[nwin];
+    const uint32_t p0 = blockIdx.x * 128u;
+    if (p0 >= total_tasks) return;
+    {
+        uint32_t p = p0 + threadIdx.x, len = 0;
+        if (p < total_tasks) {
+            uint2 tk = tasks[p];
+            uint32_t cnt = counts[tk.x], start = tk.y * TASK_LEN;
+            len = min(TASK_LEN, cnt - start) + 1;            // +1: empty tasks still sort above padding
+        }
+        s_key[threadIdx.x] = (len << 8) | threadIdx.x;
+        __syncthreads();
+        // bitonic sort of 128 keys, descending
+        for (uint32_t k = 2; k <= 128; k <<= 1) {
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                uint32_t i = threadIdx.x, ixj = i ^ j;
+                if (ixj > i) {
+                    uint32_t a = s_key[i], b = s_key[ixj];
+                    bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) { s_key[i] = b; s_key[ixj] = a; }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    const uint32_t key = s_key[threadIdx.x];
+    if ((key >> 8) == 0) return;                               // padding slot
+    const uint32_t p = p0 + (key & 0xff);
+    const uint2 tk = tasks[p];
+    const uint32_t t = tk.x, w = t / nbuckets;
+    const uint32_t cnt = counts[t], start = tk.y * TASK_LEN;
+    const uint32_t len = min(TASK_LEN, cnt - start);
+    const uint32_t *idx = sorted + (size_t)w * n + offsets[t] + start;
     ge_p3 acc; ge_p3_identity(acc);
-    for (uint32_t k = 0; k < cnt; k++) {
+    for (uint32_t k = 0; k < len; k++) {
         uint32_t e = idx[k];
         uint32_t neg = e >> 31, pi = e & 0x7fffffffu;
         if (KIND == PK_NIELS) {
@@ -217,16 +328,11 @@ k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict_
         }
     }
     ge_p3_raw r; ge_p3_store_raw(r, acc);
-    uint4 *o = reinterpret_cast<uint4 *>(buckets + t);
+    uint4 *o = reinterpret_cast<uint4 *>(ntasks[t] == 1 ? buckets + t : task_sums + p);
 #pragma unroll
     for (int q = 0; q < 10; q++) o[q] = make_uint4(r.w[4 * q], r.w[4 * q + 1], r.w[4 * q + 2], r.w[4 * q + 3]);
 }
 
-// ------------------------------------------------------------------------------------------
-// weighted bucket reduction.  State at a level: items S_j and plain-sum carries V_j with
-//   target = M * sum_j j*S_j + sum_j V_j          (0-based weights; M = product of earlier chunk sizes)
-// One thread folds a chunk of m items:  S'_q = sum_r S_{qm+r},
-//   V'_q = sum_r V_{qm+r} + M * sum_r r*S_{qm+r}   (running sums, pippenger.rs:146-151)
 __device__ __forceinline__ void load_p3(ge_p3 &p, const ge_p3_raw *src)
 {
     const uint4 *s = reinterpret_cast<const uint4 *>(src);
@@ -235,68 +341,144 @@ __device__ __forceinline__ void load_p3(ge_p3 &p, const ge_p3_raw *src)
     for (int q = 0; q < 10; q++) { uint4 v = s[q]; r.w[4 * q] = v.x; r.w[4 * q + 1] = v.y; r.w[4 * q + 2] = v.z; r.w[4 * q + 3] = v.w; }
     ge_p3_load_raw(p, r);
 }
-__device__ __forceinline__ void store_p3(ge_p3_raw *dst, const ge_p3 &p)
-{
-    ge_p3_raw r; ge_p3_store_raw(r, p);
-    uint4 *o = reinterpret_cast<uint4 *>(dst);
-#pragma unroll
-    for (int q = 0; q < 10; q++) o[q] = make_uint4(r.w[4 * q], r.w[4 * q + 1], r.w[4 * q + 2], r.w[4 * q + 3]);
-}
 
-__global__ void __launch_bounds__(64)
-k_reduce_level(const ge_p3_raw *__restrict__ S_in, const ge_p3_raw *__restrict__ V_in, uint32_t n_in, uint32_t m,
-               int log2M, uint32_t n_out, uint32_t nwin, ge_p3_raw *__restrict__ S_out, ge_p3_raw *__restrict__ V_out)
+// Everything below is latency-bound tree work on few points: it runs on groups of four lanes
+// (warp4.cuh), one point operation per group at a time.
+
+// One warp per heavy bucket (grid-stride over the heavy list): the 8 groups of the warp take
+// strided task sums, then a 3-level shuffle tree across groups.
+__global__ void __launch_bounds__(128)
+k_heavy_fixup(const uint32_t *__restrict__ heavy, const uint32_t *__restrict__ ntasks, const uint32_t *__restrict__ task_off,
+              const uint32_t *__restrict__ win_base, uint32_t nbuckets, const ge_p3_raw *__restrict__ task_sums,
+              ge_p3_raw *__restrict__ buckets)
 {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_out * nwin) return;
-    uint32_t w = t / n_out, q = t % n_out;
-    const ge_p3_raw *S = S_in + (size_t)w * n_in + (size_t)q * m;
-    uint32_t cnt = min(m, n_in - q * m);
-    ge_p3 run, acc, x;
-    load_p3(run, S + (cnt - 1));
-    if (cnt > 1) {
-        acc = run;
-        for (uint32_t r = cnt - 1; r-- > 1;) {
-            load_p3(x, S + r);
-            ge_add(run, run, x);
-            ge_add(acc, acc, run);
+    const uint32_t lane = threadIdx.x & 31, role = lane & 3, grp = lane >> 2;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nheavy = heavy[0];
+    for (uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < nheavy; h += nwarps) {
+        uint32_t tb = heavy[1 + h];
+        uint32_t kk = ntasks[tb];
+        uint32_t base = win_base[tb / nbuckets] + task_off[tb];
+        w4_point acc, x;
+        w4_identity(acc);
+        for (uint32_t j0 = 0; j0 < kk; j0 += 8) {          // uniform trip count across the warp
+            uint32_t j = j0 + grp;
+            if (j < kk) w4_load(x, task_sums + base + j); else w4_identity(x);
+            w4_add(acc, x, role);
         }
-        load_p3(x, S);
-        ge_add(run, run, x);
-        if (log2M > 0) ge_mul_by_pow_2(acc, acc, log2M);
+        for (int d = 16; d >= 4; d >>= 1) { w4_shfl_down(x, acc, d); w4_add(acc, x, role); }
+        if (grp == 0) w4_store(buckets + tb, acc, role);
+    }
+}
+
+// Bucket reduction  sum_b (b+1) B_b  per window (pippenger.rs:146-151), in log depth:
+//   level 1   chunks of m buckets: S_q = sum_r B_{qm+r},  W_q = sum_r (r+1) B_{qm+r}   (running sums)
+//   level l   chunks of m items of S^{l-1}: S^l_q, W^l_q = sum_r r S^{l-1}_{qm+r}      (0-based weights)
+//   then      target = A_1 + m_1 (A_2 + m_2 (A_3 + ...)),  A_l = plain sum of the W^l array
+// Doublings happen once per level in the final per-window Horner, not inside every level.
+// One 4-lane group per chunk; n_in is a power of two and m divides it, so every chunk has m items.
+__global__ void __launch_bounds__(128)
+k_chunk_reduce(const ge_p3_raw *__restrict__ S_in, uint32_t n_in, uint32_t m, uint32_t one_based, uint32_t n_out,
+               uint32_t nwin, ge_p3_raw *__restrict__ S_out, ge_p3_raw *__restrict__ W_out)
+{
+    const uint32_t role = threadIdx.x & 3;
+    const uint32_t total = n_out * nwin;
+    uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (((blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) >> 2) >= total) return;    // whole warp out of range
+    const bool live = t < total;
+    if (!live) t = total - 1;                                                       // keep the warp converged
+    const uint32_t w = t / n_out, q = t % n_out;
+    const ge_p3_raw *S = S_in + (size_t)w * n_in + (size_t)q * m;
+    w4_point run, acc, x;
+    w4_load(run, S + (m - 1));
+    acc = run;
+    for (uint32_t r = m - 1; r-- > 1;) {
+        w4_load(x, S + r);
+        w4_add(run, x, role);
+        w4_add(acc, run, role);
+    }
+    if (m > 1) {
+        w4_load(x, S);
+        w4_add(run, x, role);
+        if (one_based) w4_add(acc, run, role);
+    } else if (!one_based) {
+        w4_identity(acc);
+    }
+    if (live) { w4_store(S_out + t, run, role); w4_store(W_out + t, acc, role); }
+}
+
+// plain sum of one array per CTA (blockIdx.x = array id): 32 groups take strided items, then a
+// shared-memory tree over the 32 partial sums
+struct SumArrays { uint32_t off[64]; uint32_t len[64]; };
+__global__ void __launch_bounds__(128)
+k_plain_sum(const ge_p3_raw *__restrict__ pool, SumArrays arrs, ge_p3_raw *__restrict__ out)
+{
+    __shared__ ge_p3_raw sh[32];
+    const uint32_t role = threadIdx.x & 3, grp = threadIdx.x >> 2;
+    const ge_p3_raw *a = pool + arrs.off[blockIdx.x];
+    const uint32_t len = arrs.len[blockIdx.x];
+    w4_point acc, x;
+    w4_identity(acc);
+    for (uint32_t i0 = 0; i0 < len; i0 += 32) {
+        uint32_t i = i0 + grp;
+        if (i < len) w4_load(x, a + i); else w4_identity(x);
+        w4_add(acc, x, role);
+    }
+    w4_store(&sh[grp], acc, role);
+    __syncthreads();
+    for (uint32_t d = 16; d > 0; d >>= 1) {
+        if (threadIdx.x < 32 * ((d + 7) / 8)) {            // whole warps only
+            uint32_t g2 = grp < d ? grp + d : grp;        // idle groups add their own value (discarded)
+            w4_load(acc, &sh[grp]); w4_load(x, &sh[g2]);
+            w4_add(acc, x, role);
+        }
+        __syncthreads();
+        if (grp < d) w4_store(&sh[grp], acc, role);
+        __syncthreads();
+    }
+    if (grp == 0) { w4_load(acc, &sh[0]); w4_store(out + blockIdx.x, acc, role); }
+}
+
+// per window: target = A_1 + m_1 (A_2 + m_2 (...)); A sums are laid out [level][window]
+struct LevelInfo { int nlevels; int log2m[16]; };
+__global__ void __launch_bounds__(128)
+k_finish_windows(const ge_p3_raw *__restrict__ S_top, const ge_p3_raw *__restrict__ A, LevelInfo li, uint32_t nwin,
+                 ge_p3_raw *__restrict__ out)
+{
+    const uint32_t role = threadIdx.x & 3;
+    uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (((blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) >> 2) >= nwin) return;
+    const bool live = w < nwin;
+    if (!live) w = nwin - 1;
+    w4_point t, x;
+    if (li.nlevels > 0) {
+        w4_load(t, A + (size_t)(li.nlevels - 1) * nwin + w);
+        for (int l = li.nlevels - 2; l >= 0; l--) {
+            for (int k = 0; k < li.log2m[l]; k++) w4_dbl(t, role, k == li.log2m[l] - 1);
+            w4_load(x, A + (size_t)l * nwin + w);
+            w4_add(t, x, role);
+        }
     } else {
-        ge_p3_identity(acc);
+        w4_load(t, S_top + w);            // a single bucket of weight 1
     }
-    if (V_in) {
-        const ge_p3_raw *V = V_in + (size_t)w * n_in + (size_t)q * m;
-        for (uint32_t r = 0; r < cnt; r++) { load_p3(x, V + r); ge_add(acc, acc, x); }
-    }
-    store_p3(S_out + t, run);
-    store_p3(V_out + t, acc);
+    if (live) w4_store(out + w, t, role);
 }
 
-// window accumulator = sum_j (j+1) B_j = V_top + S_top
-__global__ void k_finish_windows(const ge_p3_raw *__restrict__ S_top, const ge_p3_raw *__restrict__ V_top, uint32_t nwin,
-                                 ge_p3_raw *__restrict__ out)
+// Final Horner over windows (pippenger.rs:159): total = total * 2^c + window, ~250 sequential
+// doublings on one 4-lane group, then encode.
+__global__ void __launch_bounds__(32)
+k_combine(const ge_p3_raw *__restrict__ windows, int ranks, int nwin, int c, MsmResult *__restrict__ res)
 {
-    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nwin) return;
-    ge_p3 s, v;
-    load_p3(s, S_top + w);
-    if (V_top) { load_p3(v, V_top + w); ge_add(s, s, v); }
-    store_p3(out + w, s);
-}
-
-// Horner over windows (pippenger.rs:159) for the sum over `ranks` shards, then encode.
-__global__ void k_combine(const ge_p3_raw *__restrict__ windows, int ranks, int nwin, int c, MsmResult *__restrict__ res)
-{
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    ge_p3 total, x;
-    ge_p3_identity(total);
+    const uint32_t role = threadIdx.x & 3;
+    w4_point tot, x;
+    w4_identity(tot);
     for (int w = nwin - 1; w >= 0; w--) {
-        if (w != nwin - 1) ge_mul_by_pow_2(total, total, c);
-        for (int r = 0; r < ranks; r++) { load_p3(x, windows + (size_t)r * nwin + w); ge_add(total, total, x); }
+        if (w != nwin - 1)
+            for (int k = 0; k < c; k++) w4_dbl(tot, role, k == c - 1);
+        for (int r = 0; r < ranks; r++) { w4_load(x, windows + (size_t)r * nwin + w); w4_add(tot, x, role); }
     }
+    if (threadIdx.x != 0) return;
+    ge_p3 total; total.X = tot.X; total.Y = tot.Y; total.Z = tot.Z; total.T = tot.T;
     uint32_t s[8];
     ge_compress(s, total);
 #pragma unroll
@@ -314,62 +496,111 @@ int msm_window_sums(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *
     const int nwin = msm_window_count_for_bits(c);
     const uint32_t nb = 1u << (c - 1);
     const size_t total_buckets = (size_t)nwin * nb;
+    const size_t max_tasks = total_buckets + (std::max<size_t>(1, n) * nwin) / TASK_LEN + 1;
     cudaStream_t st = ctx->stream;
     int rc;
-    if ((rc = ws_reserve(ctx, ctx->counts, total_buckets * 4))) return rc;
-    if ((rc = ws_reserve(ctx, ctx->offsets, total_buckets * 4))) return rc;
+    const size_t max_heavy = (std::max<size_t>(1, n) * nwin) / TASK_LEN + 1;
+    const uint32_t parts = (nb + SCAN_PART - 1) / SCAN_PART;
+    // counts | heavy list (count + entries): one memset clears both
+    if ((rc = ws_reserve(ctx, ctx->counts, total_buckets * 4 + (1 + max_heavy) * 4))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->offsets, total_buckets * 4 + (size_t)nwin * parts * 4))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->ntasks, total_buckets * 4))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->task_off, total_buckets * 4 + (nwin + 1) * 4))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->tasks, max_tasks * 8))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->task_sums, max_tasks * sizeof(ge_p3_raw)))) return rc;
     if ((rc = ws_reserve(ctx, ctx->digits, std::max<size_t>(1, n) * nwin * 8))) return rc;
     if ((rc = ws_reserve(ctx, ctx->sorted, std::max<size_t>(1, n) * nwin * 4))) return rc;
     if ((rc = ws_reserve(ctx, ctx->buckets, total_buckets * sizeof(ge_p3_raw)))) return rc;
     uint32_t *counts = (uint32_t *)ctx->counts.p, *offsets = (uint32_t *)ctx->offsets.p;
+    uint32_t *ntasks = (uint32_t *)ctx->ntasks.p, *task_off = (uint32_t *)ctx->task_off.p;
+    uint32_t *win_base = task_off + total_buckets;
+    uint32_t *heavy = counts + total_buckets;
+    uint32_t *part_sums = offsets + total_buckets;
+    uint2 *tasks = (uint2 *)ctx->tasks.p;
+    ge_p3_raw *task_sums = (ge_p3_raw *)ctx->task_sums.p;
     uint64_t *entries = (uint64_t *)ctx->digits.p;
     uint32_t *sorted = (uint32_t *)ctx->sorted.p;
     ge_p3_raw *buckets = (ge_p3_raw *)ctx->buckets.p;
 
-    CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, total_buckets * 4, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (total_buckets + 1) * 4, st));
     if (n) {
         k_digits<<<cdiv(n, 256), 256, 0, st>>>((const uint4 *)d_scalars, n, c, nwin, nb, counts, entries);
         ctx->launches++;
     }
-    k_scan_window<<<nwin, 1024, 0, st>>>(counts, offsets, nb);
-    ctx->launches++;
+    k_scan_partial<<<nwin * parts, 1024, 0, st>>>(counts, nb, parts, part_sums);
+    k_scan_bases<<<nwin, 32, 0, st>>>(part_sums, parts);
+    k_scan_apply<<<nwin * parts, 1024, 0, st>>>(counts, part_sums, nb, parts, offsets);
+    k_task_count<<<cdiv(total_buckets, 256), 256, 0, st>>>(counts, (uint32_t)total_buckets, ntasks, heavy);
+    k_scan_partial<<<nwin * parts, 1024, 0, st>>>(ntasks, nb, parts, part_sums);
+    k_scan_bases<<<nwin, 32, 0, st>>>(part_sums, parts);
+    k_scan_apply<<<nwin * parts, 1024, 0, st>>>(ntasks, part_sums, nb, parts, task_off);
+    k_task_bases<<<1, 32, 0, st>>>(ntasks, task_off, nb, nwin, win_base);
+    k_task_fill<<<cdiv(total_buckets, 256), 256, 0, st>>>(ntasks, task_off, win_base, nb, (uint32_t)total_buckets, tasks);
+    ctx->launches += 9;
     if (n) {
         k_scatter<<<cdiv(n, 256), 256, 0, st>>>(entries, offsets, n, nwin, nb, sorted);
         ctx->launches++;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st));
     if (point_kind == PK_NIELS)
-        k_bucket_accumulate<PK_NIELS><<<cdiv(total_buckets, 128), 128, 0, st>>>(d_points, sorted, counts, offsets, n, nb, (uint32_t)total_buckets, buckets);
+        k_bucket_accumulate<PK_NIELS><<<cdiv(max_tasks, 128), 128, 0, st>>>(d_points, sorted, counts, offsets, ntasks, tasks, win_base, nwin, n, nb, buckets, task_sums);
     else
-        k_bucket_accumulate<PK_PNIELS><<<cdiv(total_buckets, 128), 128, 0, st>>>(d_points, sorted, counts, offsets, n, nb, (uint32_t)total_buckets, buckets);
+        k_bucket_accumulate<PK_PNIELS><<<cdiv(max_tasks, 128), 128, 0, st>>>(d_points, sorted, counts, offsets, ntasks, tasks, win_base, nwin, n, nb, buckets, task_sums);
     ctx->launches++;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, st));
     ctx->last_kernel_launches = 1;
+    k_heavy_fixup<<<ctx->sm_count * 4, 128, 0, st>>>(heavy, ntasks, task_off, win_base, nb, task_sums, buckets);
+    ctx->launches++;
 
-    // reduction levels
+    // reduction: chunk levels
+    LevelInfo li; li.nlevels = 0;
+    SumArrays arrs;
+    // pool layout: for each level, S array then W array (each n_out * nwin points)
+    size_t pool_pts = 0;
+    {
+        uint32_t n_in = nb; bool first = true;
+        while (n_in > 1) {
+            uint32_t m = first ? std::min<uint32_t>(n_in, 16) : std::min<uint32_t>(n_in, 8);
+            uint32_t n_out = (n_in + m - 1) / m;
+            pool_pts += 2 * (size_t)n_out * nwin;
+            n_in = n_out; first = false;
+        }
+    }
+    if ((rc = ws_reserve(ctx, ctx->red_a, std::max<size_t>(1, pool_pts) * sizeof(ge_p3_raw)))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->red_b, (size_t)16 * nwin * sizeof(ge_p3_raw)))) return rc;
+    ge_p3_raw *pool = (ge_p3_raw *)ctx->red_a.p, *A = (ge_p3_raw *)ctx->red_b.p;
+    const ge_p3_raw *S_in = buckets;
     uint32_t n_in = nb;
-    int log2M = 0;
-    const ge_p3_raw *S_in = buckets, *V_in = nullptr;
-    DevBuf *bufs[4] = {&ctx->red_a, &ctx->red_b, &ctx->red_c, &ctx->red_d};
-    int flip = 0;
+    size_t pos = 0;
     bool first = true;
+    std::vector<std::pair<size_t, uint32_t>> w_arrays;    // (offset of W array, n_out) per level
     while (n_in > 1) {
         uint32_t m = first ? std::min<uint32_t>(n_in, 16) : std::min<uint32_t>(n_in, 8);
         uint32_t n_out = (n_in + m - 1) / m;
-        DevBuf *bs = bufs[flip], *bv = bufs[flip + 1];
-        if ((rc = ws_reserve(ctx, *bs, (size_t)n_out * nwin * sizeof(ge_p3_raw)))) return rc;
-        if ((rc = ws_reserve(ctx, *bv, (size_t)n_out * nwin * sizeof(ge_p3_raw)))) return rc;
-        k_reduce_level<<<cdiv((size_t)n_out * nwin, 64), 64, 0, st>>>(S_in, V_in, n_in, m, log2M, n_out, nwin,
-                                                                       (ge_p3_raw *)bs->p, (ge_p3_raw *)bv->p);
+        ge_p3_raw *S_out = pool + pos, *W_out = pool + pos + (size_t)n_out * nwin;
+        k_chunk_reduce<<<cdiv((size_t)n_out * nwin * 4, 128), 128, 0, st>>>(S_in, n_in, m, first ? 1u : 0u, n_out, nwin, S_out, W_out);
         ctx->launches++;
-        S_in = (const ge_p3_raw *)bs->p; V_in = (const ge_p3_raw *)bv->p;
+        w_arrays.push_back({pos + (size_t)n_out * nwin, n_out});
         int lg = 0; while ((1u << lg) < m) lg++;
-        log2M += lg;
-        n_in = n_out;
-        flip = 2 - flip;
-        first = false;
+        li.log2m[li.nlevels++] = lg;
+        S_in = S_out; n_in = n_out; pos += 2 * (size_t)n_out * nwin; first = false;
     }
-    k_finish_windows<<<cdiv(nwin, 64), 64, 0, st>>>(S_in, V_in, nwin, d_windows);
+    // plain sums of every (level, window) W array: one CTA each, at most 64 arrays per launch
+    {
+        int total = li.nlevels * nwin, done = 0;
+        while (done < total) {
+            int batch = std::min(64, total - done);
+            for (int k = 0; k < batch; k++) {
+                int id = done + k, l = id / nwin, w = id % nwin;
+                arrs.off[k] = (uint32_t)(w_arrays[l].first + (size_t)w * w_arrays[l].second);
+                arrs.len[k] = w_arrays[l].second;
+            }
+            k_plain_sum<<<batch, 128, 0, st>>>(pool, arrs, A + done);
+            ctx->launches++;
+            done += batch;
+        }
+    }
+    k_finish_windows<<<cdiv((size_t)nwin * 4, 128), 128, 0, st>>>(S_in, A, li, nwin, d_windows);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
