@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -182,6 +182,7 @@ def run_msm(args, rank, world, local):
 
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("DALEK_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = pkg.Engine(local)
     n_local = args.pairs_per_gpu or ((1 << 20) if world == 1 else (1 << 21))
@@ -328,6 +329,7 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None):
     warmup = args.warmup if warmup is None else warmup
     torch.cuda.set_device(local)
     if world > 1 and not dist.is_initialized():
+        os.environ["NCCL_DEBUG"] = os.environ.get("DALEK_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = eng or pkg.Engine(local)
     n = args.sigs_per_gpu or (1 << 22)
@@ -407,6 +409,28 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None):
                      "bucket_kernel_ms": kms, "note": "integer-multiply bound (decompression + MSM)"},
         "clocks": clocks,
     }
+
+
+def run_double_base(eng, n=1 << 20, steps=3):
+    """BASELINE configs[4]: RistrettoPoint::multiscalar_mul([a_i, b_i], [G, H]) for 2^20 pairs (constant-time
+    contract), host buffers in, compressed points out (64 B in + 32 B out per pair)."""
+    import numpy as np
+    a, b = fast_scalars(n, seed=31), fast_scalars(n, seed=32)
+    _, Gc = eng.mul_base_batch(np.frombuffer((1).to_bytes(32, "little"), dtype=np.uint8).copy(), 1)
+    # Ristretto basepoint encoding (curve25519-dalek/src/constants.rs:57-60) and H = h*G via the engine itself
+    G = bytes.fromhex("e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76")
+    h = np.frombuffer(hashlib.sha512(b"dalek-b200/H").digest()[:32], dtype=np.uint8).copy(); h[31] &= 0x0F
+    rc, H = eng.ristretto_double_base_batch(np.zeros(32, dtype=np.uint8), h, G, G, 1)
+    assert rc == 0
+    eng.ristretto_double_base_batch(a, b, G, H, n)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rc, out = eng.ristretto_double_base_batch(a, b, G, H, n)
+    dt = (time.perf_counter() - t0) / steps
+    assert rc == 0
+    return {"metric": "Ristretto double-base (aG+bH) pairs/sec, host buffers", "value": n / dt, "unit": "pairs/s",
+            "ms_per_step": dt * 1e3, "kernel_ms": eng.last_kernel_ms()[0], "pairs": n,
+            "checksum": hashlib.sha256(out).hexdigest()[:16]}
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline (oracle)
@@ -503,7 +527,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="msm", choices=["msm", "verify"])
@@ -531,6 +555,7 @@ def main():
         if not args.no_extras and world == 1:
             v = run_verify(args, rank, world, local, eng=eng, steps=min(args.steps, 5), warmup=3)
             line["verify_batch"] = {k: v[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "config", "gpu_launches", "roofline")}
+            line["ristretto_double_base"] = run_double_base(eng)
     if rank == 0 and world == 1 and not args.no_extras:
         threads = 1
         if args.workload == "verify":

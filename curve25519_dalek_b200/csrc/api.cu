@@ -23,11 +23,18 @@ int dalek_b200_init(int device, dalek_b200_ctx **out)
     if (!ctx) return DALEK_E_NOMEM;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);       // (greatest priority is the lower number)
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_grp[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_grp[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_grp[2], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_grp[3], cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return DALEK_E_CUDA;
     }
@@ -48,6 +55,8 @@ void dalek_b200_destroy(dalek_b200_ctx *ctx)
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    cudaEventDestroy(ctx->ev_join2);
+    for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev_grp[i]);
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2);
     delete ctx;
 }
@@ -58,6 +67,8 @@ int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value)
 {
     if (!ctx || !name) return DALEK_E_INVALID_ARG;
     if (!strcmp(name, "window_bits")) { if (value != 0 && (value < 4 || value > 20)) return DALEK_E_INVALID_ARG; ctx->opt_window_bits = value; return 0; }
+    if (!strcmp(name, "window_groups")) { if (value < 1 || value > 4) return DALEK_E_INVALID_ARG; ctx->opt_window_groups = value; return 0; }
+    if (!strcmp(name, "field_f64")) { ctx->opt_field_f64 = value ? 1 : 0; return 0; }
     if (!strcmp(name, "verify_chunk")) { if (value < 1 || value > (1 << 20)) return DALEK_E_INVALID_ARG; ctx->opt_verify_chunk = value; return 0; }
     return DALEK_E_INVALID_ARG;
 }
@@ -79,7 +90,7 @@ static size_t point_in_bytes(int fmt) { return fmt == DALEK_POINTS_COMPRESSED ? 
 
 // device scalars/points -> window sums in ctx->red? -> result.  Returns reference-level code.
 static int run_msm_dev(dalek_b200_ctx *ctx, const void *d_scalars, const void *d_points_in, int point_fmt, size_t n,
-                       size_t n_total, ge_p3_raw *d_windows, int *bad_out)
+                       size_t n_total, ge_p3_raw *d_windows, int *bad_out, MsmResult *d_result = nullptr)
 {
     int rc;
     const int kind = point_fmt == DALEK_POINTS_COMPRESSED ? PK_NIELS : PK_PNIELS;
@@ -89,7 +100,8 @@ static int run_msm_dev(dalek_b200_ctx *ctx, const void *d_scalars, const void *d
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->flags.p, 0, 64, ctx->stream));
     if ((rc = msm_prepare_points(ctx, d_points_in, point_fmt, n, ctx->points.p, (int *)ctx->flags.p))) return rc;
     int c = msm_choose_window_bits(ctx, n_total);
-    if ((rc = msm_window_sums(ctx, (const uint32_t *)d_scalars, ctx->points.p, kind, n, c, d_windows))) return rc;
+    if (d_result) { if ((rc = msm_full(ctx, (const uint32_t *)d_scalars, ctx->points.p, kind, n, c, d_windows, d_result))) return rc; }
+    else if ((rc = msm_window_sums(ctx, (const uint32_t *)d_scalars, ctx->points.p, kind, n, c, d_windows))) return rc;
     if (bad_out) {
         CUDA_TRY(ctx, cudaMemcpyAsync(bad_out, ctx->flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -97,13 +109,13 @@ static int run_msm_dev(dalek_b200_ctx *ctx, const void *d_scalars, const void *d
 }
 
 static int finish_msm(dalek_b200_ctx *ctx, const ge_p3_raw *d_windows, int ranks, size_t n_total,
-                      uint8_t out_compressed[32], uint64_t out_limbs[20], uint32_t *is_identity)
+                      uint8_t out_compressed[32], uint64_t out_limbs[20], uint32_t *is_identity, bool already_combined = false)
 {
     int rc;
     int c = msm_choose_window_bits(ctx, n_total);
     int nwin = msm_window_count_for_bits(c);
     if ((rc = ws_reserve(ctx, ctx->result, sizeof(MsmResult)))) return rc;
-    if ((rc = msm_combine_windows(ctx, d_windows, ranks, nwin, c, (MsmResult *)ctx->result.p))) return rc;
+    if (!already_combined && (rc = msm_combine_windows(ctx, d_windows, ranks, nwin, c, (MsmResult *)ctx->result.p))) return rc;
     if ((rc = pinned_reserve(ctx, sizeof(MsmResult) + 64))) return rc;
     MsmResult *h = (MsmResult *)ctx->h_pinned;
     CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->result.p, sizeof(MsmResult), cudaMemcpyDeviceToHost, ctx->stream));
@@ -140,8 +152,9 @@ static int msm_common(dalek_b200_ctx *ctx, const void *scalars, const void *poin
     if ((rc = pinned_reserve(ctx, sizeof(MsmResult) + 64))) return rc;
     int *h_bad = (int *)((char *)ctx->h_pinned + sizeof(MsmResult));
     *h_bad = 0;
-    if ((rc = run_msm_dev(ctx, d_s, d_p, point_fmt, n, n, (ge_p3_raw *)ctx->misc0.p, h_bad))) return rc;
-    if ((rc = finish_msm(ctx, (const ge_p3_raw *)ctx->misc0.p, 1, n, out_compressed, out_limbs, nullptr))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->result, sizeof(MsmResult)))) return rc;
+    if ((rc = run_msm_dev(ctx, d_s, d_p, point_fmt, n, n, (ge_p3_raw *)ctx->misc0.p, h_bad, (MsmResult *)ctx->result.p))) return rc;
+    if ((rc = finish_msm(ctx, (const ge_p3_raw *)ctx->misc0.p, 1, n, out_compressed, out_limbs, nullptr, true))) return rc;
     return *h_bad ? DALEK_NONE : DALEK_OK;
 }
 

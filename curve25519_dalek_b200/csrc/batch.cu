@@ -218,20 +218,26 @@ static int verify_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t
     int *flags = (int *)ctx->flags.p;
     uint32_t *scalars = (uint32_t *)ctx->scalars.p;
     CUDA_TRY(ctx, cudaMemsetAsync(flags, 0, 64, st));
-    // decompression runs on the second stream, concurrently with hashing / transcript / coefficients
+    // Two streams: the hashing -> transcript -> coefficient chain (a long dependency chain with little
+    // parallelism in the transcript) is enqueued first on the high-priority stream; decompression
+    // (plenty of independent work, bound by the integer-multiply pipe) fills the machine from the
+    // second stream while the sponges run.
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
-    k_prep_RA<<<cdiv(m, 128), 128, 0, st2>>>(d_sigs, d_keys, n, (ge_niels_packed *)ctx->points.p, flags);
-    ctx->launches++;
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, st2));
     if (n) {
         k_hram<<<cdiv(n, 128), 128, 0, st>>>(d_msgs, d_offs, d_sigs, d_keys, n, (uint32_t *)ctx->misc2.p,
                                              (uint32_t *)ctx->misc3.p, flags);
         size_t nchunks = (n + chunk - 1) / chunk;
         k_transcript<<<cdiv(nchunks, 64), 64, 0, st>>>((const uint32_t *)ctx->misc2.p, d_sigs, n, chunk, (uint32_t *)ctx->zs.p);
+        ctx->launches += 2;
+    }
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
+    k_prep_RA<<<cdiv(m, 128), 128, 0, st2>>>(d_sigs, d_keys, n, (ge_niels_packed *)ctx->points.p, flags);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, st2));
+    if (n) {
         k_coeffs<<<cdiv(n, 128), 128, 0, st>>>((const uint32_t *)ctx->zs.p, d_sigs, (const uint32_t *)ctx->misc3.p, n,
                                                scalars, (uint32_t *)ctx->misc4.p);
-        ctx->launches += 3;
+        ctx->launches++;
     }
     k_sum_partial<<<cdiv(nsum, 128), 128, 0, st>>>((const uint32_t *)ctx->misc4.p, n, nsum, (uint32_t *)ctx->misc5.p);
     k_sum_final<<<1, 256, 0, st>>>((const uint32_t *)ctx->misc5.p, nsum, scalars);
@@ -243,8 +249,7 @@ static int verify_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t
     int nwin = msm_window_count_for_bits(c);
     if ((rc = ws_reserve(ctx, ctx->misc0, (size_t)nwin * sizeof(ge_p3_raw)))) return rc;
     if ((rc = ws_reserve(ctx, ctx->result, sizeof(MsmResult)))) return rc;
-    if ((rc = msm_window_sums(ctx, scalars, ctx->points.p, PK_NIELS, m, c, (ge_p3_raw *)ctx->misc0.p))) return rc;
-    if ((rc = msm_combine_windows(ctx, (const ge_p3_raw *)ctx->misc0.p, 1, nwin, c, (MsmResult *)ctx->result.p))) return rc;
+    if ((rc = msm_full(ctx, scalars, ctx->points.p, PK_NIELS, m, c, (ge_p3_raw *)ctx->misc0.p, (MsmResult *)ctx->result.p))) return rc;
     if ((rc = pinned_reserve(ctx, sizeof(MsmResult) + 128))) return rc;
     MsmResult *h = (MsmResult *)ctx->h_pinned;
     int *hflags = (int *)((char *)ctx->h_pinned + sizeof(MsmResult));

@@ -19,12 +19,15 @@ struct dalek_b200_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+    cudaEvent_t ev_grp[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string last_error;
     uint64_t launches = 0;
     // options
     long opt_window_bits = 0;
     long opt_verify_chunk = 128;
+    long opt_window_groups = 1; // >1: window groups pipelined over two streams (measured slower on B200: profiles/sweep_r1.txt)
+    long opt_field_f64 = 1;     // bucket kernel on the FP64 pipe (fe64.cuh) instead of IMAD.WIDE (fe.cuh)
     // timing of the dominant kernel in the last call
     float last_kernel_ms = 0.f;
     int last_kernel_launches = 0;
@@ -70,6 +73,9 @@ int msm_window_sums(dalek_b200_ctx *ctx, const uint32_t *d_scalars /* n x 8 word
 // total = sum over ranks of windows, Horner-combined; writes compressed (8 words) + canonical
 // limbs51 (20 u64) + identity flag to d_result (layout: 8 u32 | pad | 20 u64 | u32 flag).
 struct MsmResult { uint32_t compressed[8]; uint64_t limbs[20]; uint32_t is_identity; uint32_t pad; };
+// window sums + pipelined Horner + encode in one go (single-shard case)
+int msm_full(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n, int c,
+             ge_p3_raw *d_windows, MsmResult *d_result);
 int msm_combine_windows(dalek_b200_ctx *ctx, const ge_p3_raw *d_windows, int ranks, int nwin, int c,
                         MsmResult *d_result);
 

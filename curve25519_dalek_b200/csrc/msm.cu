@@ -25,6 +25,7 @@
 
 #include "../../include/dalek_b200.h"
 #include "engine.h"
+#include "ge64.cuh"
 #include "warp4.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -226,6 +227,9 @@ __global__ void k_scatter(const uint64_t *__restrict__ entries, const uint32_t *
 // is cut into several tasks whose partial sums are added afterwards by k_heavy_fixup.  Inside a
 // CTA the 128 tasks are sorted by length so that the lanes of a warp run the same trip count.
 #define TASK_LEN 64u
+#ifndef ACC_MIN_BLOCKS
+#define ACC_MIN_BLOCKS 4
+#endif
 
 // also appends every bucket that needs more than one task to the heavy list (heavy[0] = count)
 __global__ void k_task_count(const uint32_t *__restrict__ counts, uint32_t total_buckets, uint32_t *__restrict__ ntasks,
@@ -265,17 +269,18 @@ __global__ void k_task_fill(const uint32_t *__restrict__ ntasks, const uint32_t 
     for (uint32_t j = 0; j < k; j++) tasks[base + j] = make_uint2(t, j);
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(128, 4)
+template <int KIND, int F64>
+__global__ void __launch_bounds__(128, ACC_MIN_BLOCKS)
 k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict__ sorted,
                     const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets,
                     const uint32_t *__restrict__ ntasks, const uint2 *__restrict__ tasks,
-                    const uint32_t *__restrict__ win_base, int nwin, size_t n, uint32_t nbuckets,
+                    const uint32_t *__restrict__ win_base, int w0, int w1, size_t n, uint32_t nbuckets,
                     ge_p3_raw *__restrict__ buckets, ge_p3_raw *__restrict__ task_sums)
 {
     __shared__ uint32_t s_key[128];     // (len << 8) | local task index, sorted descending
-    const uint32_t total_tasks = win_base[nwin];
-    const uint32_t p0 = blockIdx.x * 128u;
+    __shared__ uint4 s_pts[F64 ? 2 : 1][F64 ? 8 : 1][F64 ? 128 : 1];   // prefetch slots, [buffer][piece][thread]: conflict-free
+    const uint32_t total_tasks = win_base[w1];            // this launch covers the tasks of windows [w0, w1)
+    const uint32_t p0 = win_base[w0] + blockIdx.x * 128u;
     if (p0 >= total_tasks) return;
     {
         uint32_t p = p0 + threadIdx.x, len = 0;
@@ -307,7 +312,49 @@ k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict_
     const uint32_t cnt = counts[t], start = tk.y * TASK_LEN;
     const uint32_t len = min(TASK_LEN, cnt - start);
     const uint32_t *idx = sorted + (size_t)w * n + offsets[t] + start;
-    ge_p3 acc; ge_p3_identity(acc);
+    ge_p3 acc;
+    if (F64) {
+        // FP64-pipe field (fe64.cuh): 1.65x the multiplication rate of the IMAD.WIDE form
+        // The gather of the NEXT point (128-bit cp.async into this thread's shared-memory slot, two
+        // slots per thread) is in flight while the current addition runs, so the HBM/L2 latency of the
+        // random gathers is off the dependent path.
+        constexpr int NQ = KIND == PK_NIELS ? 6 : 8;            // 16-byte pieces per point
+        ge64_p3 acc64; ge64_identity(acc64);
+        uint32_t e_next = len ? idx[0] : 0;
+        auto prefetch = [&](uint32_t e, int buf) {
+            const uint32_t pi = e & 0x7fffffffu;
+            const char *src = reinterpret_cast<const char *>(points) + (size_t)pi * (NQ * 16);
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_pts[buf][q][threadIdx.x]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 16 * q) : "memory");
+            }
+        };
+        if (len) prefetch(e_next, 0);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (uint32_t k = 0; k < len; k++) {
+            const uint32_t e = e_next, neg = e >> 31;
+            const int buf = k & 1;
+            if (k + 1 < len) { e_next = idx[k + 1]; prefetch(e_next, buf ^ 1); }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            if (KIND == PK_NIELS) {
+                ge_niels_packed pk;
+#pragma unroll
+                for (int q = 0; q < 6; q++) { uint4 v = s_pts[buf][q][threadIdx.x]; pk.w[4 * q] = v.x; pk.w[4 * q + 1] = v.y; pk.w[4 * q + 2] = v.z; pk.w[4 * q + 3] = v.w; }
+                ge64_niels nl; ge64_niels_unpack(nl, pk);
+                ge64_madd(acc64, acc64, nl, neg);
+            } else {
+                ge_pniels_packed pk;
+#pragma unroll
+                for (int q = 0; q < 8; q++) { uint4 v = s_pts[buf][q][threadIdx.x]; pk.w[4 * q] = v.x; pk.w[4 * q + 1] = v.y; pk.w[4 * q + 2] = v.z; pk.w[4 * q + 3] = v.w; }
+                ge64_pniels pn; ge64_pniels_unpack(pn, pk);
+                ge64_padd(acc64, acc64, pn, neg);
+            }
+        }
+        ge64_to_p3(acc, acc64);
+    } else {
+    ge_p3_identity(acc);
     for (uint32_t k = 0; k < len; k++) {
         uint32_t e = idx[k];
         uint32_t neg = e >> 31, pi = e & 0x7fffffffu;
@@ -326,6 +373,7 @@ k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict_
             ge_pniels pn; ge_pniels_unpack(pn, pk);
             ge_padd(acc, acc, pn, neg);
         }
+    }
     }
     ge_p3_raw r; ge_p3_store_raw(r, acc);
     uint4 *o = reinterpret_cast<uint4 *>(ntasks[t] == 1 ? buckets + t : task_sums + p);
@@ -349,14 +397,15 @@ __device__ __forceinline__ void load_p3(ge_p3 &p, const ge_p3_raw *src)
 // strided task sums, then a 3-level shuffle tree across groups.
 __global__ void __launch_bounds__(128)
 k_heavy_fixup(const uint32_t *__restrict__ heavy, const uint32_t *__restrict__ ntasks, const uint32_t *__restrict__ task_off,
-              const uint32_t *__restrict__ win_base, uint32_t nbuckets, const ge_p3_raw *__restrict__ task_sums,
-              ge_p3_raw *__restrict__ buckets)
+              const uint32_t *__restrict__ win_base, uint32_t nbuckets, uint32_t w0, uint32_t w1,
+              const ge_p3_raw *__restrict__ task_sums, ge_p3_raw *__restrict__ buckets)
 {
     const uint32_t lane = threadIdx.x & 31, role = lane & 3, grp = lane >> 2;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t nheavy = heavy[0];
     for (uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < nheavy; h += nwarps) {
         uint32_t tb = heavy[1 + h];
+        if (tb / nbuckets < w0 || tb / nbuckets >= w1) continue;      // another window group's bucket
         uint32_t kk = ntasks[tb];
         uint32_t base = win_base[tb / nbuckets] + task_off[tb];
         w4_point acc, x;
@@ -409,7 +458,7 @@ k_chunk_reduce(const ge_p3_raw *__restrict__ S_in, uint32_t n_in, uint32_t m, ui
 
 // plain sum of one array per CTA (blockIdx.x = array id): 32 groups take strided items, then a
 // shared-memory tree over the 32 partial sums
-struct SumArrays { uint32_t off[64]; uint32_t len[64]; };
+struct SumArrays { uint32_t off[160]; uint32_t len[160]; };
 __global__ void __launch_bounds__(128)
 k_plain_sum(const ge_p3_raw *__restrict__ pool, SumArrays arrs, ge_p3_raw *__restrict__ out)
 {
@@ -489,9 +538,42 @@ k_combine(const ge_p3_raw *__restrict__ windows, int ranks, int nwin, int c, Msm
     res->pad = 0;
 }
 
+// Horner continued over one window group: state = state * 2^(c * count) + ... (windows w_hi-1 .. w_lo).
+// `first` = the group holding the top window (state starts at the identity, no leading doublings).
+__global__ void __launch_bounds__(32)
+k_horner_step(ge_p3_raw *__restrict__ state, const ge_p3_raw *__restrict__ windows, int w_hi, int w_lo, int c, int first)
+{
+    const uint32_t role = threadIdx.x & 3;
+    w4_point tot, x;
+    if (first) w4_identity(tot); else w4_load(tot, state);
+    for (int w = w_hi - 1; w >= w_lo; w--) {
+        if (!(first && w == w_hi - 1))
+            for (int k = 0; k < c; k++) w4_dbl(tot, role, k == c - 1);
+        w4_load(x, windows + w);
+        w4_add(tot, x, role);
+    }
+    if (threadIdx.x < 4) w4_store(state, tot, role);
+}
+
+__global__ void k_encode(const ge_p3_raw *__restrict__ state, MsmResult *__restrict__ res)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    ge_p3 total; load_p3(total, state);
+    uint32_t s[8];
+    ge_compress(s, total);
+#pragma unroll
+    for (int i = 0; i < 8; i++) res->compressed[i] = s[i];
+    fe_to_limbs51(res->limbs, total.X); fe_to_limbs51(res->limbs + 5, total.Y);
+    fe_to_limbs51(res->limbs + 10, total.Z); fe_to_limbs51(res->limbs + 15, total.T);
+    res->is_identity = ge_is_identity(total);
+    res->pad = 0;
+}
+
 // ------------------------------------------------------------------------------------------
-int msm_window_sums(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n,
-                    int c, ge_p3_raw *d_windows)
+// Window groups (top windows first) are pipelined over two streams: while the bucket kernel works on
+// group g+1, the reduction tree and the Horner steps of group g run on the second stream.
+static int msm_pipeline(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n,
+                        int c, ge_p3_raw *d_windows, MsmResult *d_result)
 {
     const int nwin = msm_window_count_for_bits(c);
     const uint32_t nb = 1u << (c - 1);
@@ -541,69 +623,107 @@ int msm_window_sums(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *
         k_scatter<<<cdiv(n, 256), 256, 0, st>>>(entries, offsets, n, nwin, nb, sorted);
         ctx->launches++;
     }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st));
-    if (point_kind == PK_NIELS)
-        k_bucket_accumulate<PK_NIELS><<<cdiv(max_tasks, 128), 128, 0, st>>>(d_points, sorted, counts, offsets, ntasks, tasks, win_base, nwin, n, nb, buckets, task_sums);
-    else
-        k_bucket_accumulate<PK_PNIELS><<<cdiv(max_tasks, 128), 128, 0, st>>>(d_points, sorted, counts, offsets, ntasks, tasks, win_base, nwin, n, nb, buckets, task_sums);
-    ctx->launches++;
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, st));
-    ctx->last_kernel_launches = 1;
-    k_heavy_fixup<<<ctx->sm_count * 4, 128, 0, st>>>(heavy, ntasks, task_off, win_base, nb, task_sums, buckets);
-    ctx->launches++;
-
-    // reduction: chunk levels
+    // ---- window groups
+    int G = (int)ctx->opt_window_groups;
+    if (G < 1 || nwin < 2 * G || n < 8192) G = 1;        // tiny problems are launch-bound: do not split                                    // tiny problems are launch-bound: do not split
+    cudaStream_t sb = ctx->stream2;
+    // reduction scratch: level structure is the same for every window
     LevelInfo li; li.nlevels = 0;
-    SumArrays arrs;
-    // pool layout: for each level, S array then W array (each n_out * nwin points)
-    size_t pool_pts = 0;
+    std::vector<uint32_t> lvl_m, lvl_nout;
+    size_t pool_pts_per_win = 0;
     {
         uint32_t n_in = nb; bool first = true;
         while (n_in > 1) {
             uint32_t m = first ? std::min<uint32_t>(n_in, 16) : std::min<uint32_t>(n_in, 8);
             uint32_t n_out = (n_in + m - 1) / m;
-            pool_pts += 2 * (size_t)n_out * nwin;
+            lvl_m.push_back(m); lvl_nout.push_back(n_out);
+            int lg = 0; while ((1u << lg) < m) lg++;
+            li.log2m[li.nlevels++] = lg;
+            pool_pts_per_win += 2 * (size_t)n_out;
             n_in = n_out; first = false;
         }
     }
-    if ((rc = ws_reserve(ctx, ctx->red_a, std::max<size_t>(1, pool_pts) * sizeof(ge_p3_raw)))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->red_a, std::max<size_t>(1, pool_pts_per_win * nwin) * sizeof(ge_p3_raw)))) return rc;
     if ((rc = ws_reserve(ctx, ctx->red_b, (size_t)16 * nwin * sizeof(ge_p3_raw)))) return rc;
-    ge_p3_raw *pool = (ge_p3_raw *)ctx->red_a.p, *A = (ge_p3_raw *)ctx->red_b.p;
-    const ge_p3_raw *S_in = buckets;
-    uint32_t n_in = nb;
-    size_t pos = 0;
-    bool first = true;
-    std::vector<std::pair<size_t, uint32_t>> w_arrays;    // (offset of W array, n_out) per level
-    while (n_in > 1) {
-        uint32_t m = first ? std::min<uint32_t>(n_in, 16) : std::min<uint32_t>(n_in, 8);
-        uint32_t n_out = (n_in + m - 1) / m;
-        ge_p3_raw *S_out = pool + pos, *W_out = pool + pos + (size_t)n_out * nwin;
-        k_chunk_reduce<<<cdiv((size_t)n_out * nwin * 4, 128), 128, 0, st>>>(S_in, n_in, m, first ? 1u : 0u, n_out, nwin, S_out, W_out);
-        ctx->launches++;
-        w_arrays.push_back({pos + (size_t)n_out * nwin, n_out});
-        int lg = 0; while ((1u << lg) < m) lg++;
-        li.log2m[li.nlevels++] = lg;
-        S_in = S_out; n_in = n_out; pos += 2 * (size_t)n_out * nwin; first = false;
-    }
-    // plain sums of every (level, window) W array: one CTA each, at most 64 arrays per launch
-    {
-        int total = li.nlevels * nwin, done = 0;
-        while (done < total) {
-            int batch = std::min(64, total - done);
-            for (int k = 0; k < batch; k++) {
-                int id = done + k, l = id / nwin, w = id % nwin;
-                arrs.off[k] = (uint32_t)(w_arrays[l].first + (size_t)w * w_arrays[l].second);
-                arrs.len[k] = w_arrays[l].second;
-            }
-            k_plain_sum<<<batch, 128, 0, st>>>(pool, arrs, A + done);
+    if ((rc = ws_reserve(ctx, ctx->red_c, sizeof(ge_p3_raw)))) return rc;
+    ge_p3_raw *pool_all = (ge_p3_raw *)ctx->red_a.p, *A_all = (ge_p3_raw *)ctx->red_b.p, *state = (ge_p3_raw *)ctx->red_c.p;
+
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st));
+    for (int g = 0; g < G; g++) {
+        const int w1 = nwin - (nwin * g) / G, w0 = nwin - (nwin * (g + 1)) / G, nwg = w1 - w0;
+        const size_t max_tasks_g = (size_t)nwg * nb + (std::max<size_t>(1, n) * nwg) / TASK_LEN + 1;
+        const unsigned grid = cdiv(max_tasks_g, 128);
+#define LAUNCH_ACC(KIND_, F64_) k_bucket_accumulate<KIND_, F64_><<<grid, 128, 0, st>>>(d_points, sorted, counts, offsets, ntasks, tasks, win_base, w0, w1, n, nb, buckets, task_sums)
+        if (point_kind == PK_NIELS) { if (ctx->opt_field_f64) LAUNCH_ACC(PK_NIELS, 1); else LAUNCH_ACC(PK_NIELS, 0); }
+        else { if (ctx->opt_field_f64) LAUNCH_ACC(PK_PNIELS, 1); else LAUNCH_ACC(PK_PNIELS, 0); }
+#undef LAUNCH_ACC
+        k_heavy_fixup<<<ctx->sm_count * 4, 128, 0, st>>>(heavy, ntasks, task_off, win_base, nb, (uint32_t)w0, (uint32_t)w1, task_sums, buckets);
+        ctx->launches += 2;
+        if (g == G - 1) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, st));   // end of the bucket-accumulation kernels
+        cudaStream_t sr = G > 1 ? sb : st;                  // where this group's tail runs
+        if (G > 1) {
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_grp[g], st));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(sb, ctx->ev_grp[g], 0));
+        }
+        // reduction of windows [w0, w1)
+        ge_p3_raw *pool = pool_all + pool_pts_per_win * w0, *A = A_all + (size_t)16 * w0;
+        const ge_p3_raw *S_in = buckets + (size_t)w0 * nb;
+        uint32_t n_in = nb;
+        size_t pos = 0;
+        std::vector<std::pair<size_t, uint32_t>> w_arrays;
+        for (int l = 0; l < li.nlevels; l++) {
+            uint32_t m = lvl_m[l], n_out = lvl_nout[l];
+            ge_p3_raw *S_out = pool + pos, *W_out = pool + pos + (size_t)n_out * nwg;
+            k_chunk_reduce<<<cdiv((size_t)n_out * nwg * 4, 128), 128, 0, sr>>>(S_in, n_in, m, l == 0 ? 1u : 0u, n_out, nwg, S_out, W_out);
             ctx->launches++;
-            done += batch;
+            w_arrays.push_back({pos + (size_t)n_out * nwg, n_out});
+            S_in = S_out; n_in = n_out; pos += 2 * (size_t)n_out * nwg;
+        }
+        {
+            SumArrays arrs;
+            int total = li.nlevels * nwg, done = 0;
+            while (done < total) {
+                int batch = std::min(160, total - done);
+                for (int k = 0; k < batch; k++) {
+                    int id = done + k, l = id / nwg, w = id % nwg;
+                    arrs.off[k] = (uint32_t)(w_arrays[l].first + (size_t)w * w_arrays[l].second);
+                    arrs.len[k] = w_arrays[l].second;
+                }
+                k_plain_sum<<<batch, 128, 0, sr>>>(pool, arrs, A + done);
+                ctx->launches++;
+                done += batch;
+            }
+        }
+        k_finish_windows<<<cdiv((size_t)nwg * 4, 128), 128, 0, sr>>>(S_in, A, li, nwg, d_windows + w0);
+        ctx->launches++;
+        if (d_result) {
+            k_horner_step<<<1, 32, 0, sr>>>(state, d_windows, w1, w0, c, g == 0);
+            ctx->launches++;
         }
     }
-    k_finish_windows<<<cdiv((size_t)nwin * 4, 128), 128, 0, st>>>(S_in, A, li, nwin, d_windows);
-    ctx->launches++;
+    ctx->last_kernel_launches = G;
+    if (G > 1) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join2, sb));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join2, 0));
+    }
+    if (d_result) {
+        k_encode<<<1, 32, 0, st>>>(state, d_result);
+        ctx->launches++;
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
+}
+
+int msm_window_sums(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n,
+                    int c, ge_p3_raw *d_windows)
+{
+    return msm_pipeline(ctx, d_scalars, d_points, point_kind, n, c, d_windows, nullptr);
+}
+
+int msm_full(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n, int c,
+             ge_p3_raw *d_windows, MsmResult *d_result)
+{
+    return msm_pipeline(ctx, d_scalars, d_points, point_kind, n, c, d_windows, d_result);
 }
 
 int msm_combine_windows(dalek_b200_ctx *ctx, const ge_p3_raw *d_windows, int ranks, int nwin, int c, MsmResult *d_result)

@@ -368,8 +368,7 @@ int dalek_b200_ristretto_vartime_msm(dalek_b200_ctx *ctx, const uint8_t *scalars
     int c = msm_choose_window_bits(ctx, n);
     int nwin = msm_window_count_for_bits(c);
     if ((rc = ws_reserve(ctx, ctx->misc0, (size_t)nwin * sizeof(ge_p3_raw)))) return rc;
-    if ((rc = msm_window_sums(ctx, (const uint32_t *)ctx->scalars.p, ctx->points.p, PK_PNIELS, n, c, (ge_p3_raw *)ctx->misc0.p))) return rc;
-    if ((rc = msm_combine_windows(ctx, (const ge_p3_raw *)ctx->misc0.p, 1, nwin, c, (MsmResult *)ctx->result.p))) return rc;
+    if ((rc = msm_full(ctx, (const uint32_t *)ctx->scalars.p, ctx->points.p, PK_PNIELS, n, c, (ge_p3_raw *)ctx->misc0.p, (MsmResult *)ctx->result.p))) return rc;
     uint32_t *d_enc = (uint32_t *)((char *)ctx->result.p + sizeof(MsmResult));
     k_ristretto_encode_result<<<1, 1, 0, st>>>((const MsmResult *)ctx->result.p, d_enc);
     ctx->launches++;

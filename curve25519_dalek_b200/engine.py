@@ -10,7 +10,8 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(HERE, "libdalek_b200.so")
+    # DALEK_B200_LIB selects an alternative build of the same engine (tuning experiments only)
+    return os.environ.get("DALEK_B200_LIB") or os.path.join(HERE, "libdalek_b200.so")
 
 
 def load_library():

@@ -83,3 +83,38 @@ int h_ristretto_roundtrip(uint8_t *out, uint8_t *out_dbl, const uint8_t *in)
     return 1;
 }
 }
+#include "../../curve25519_dalek_b200/csrc/ge64.cuh"
+extern "C" {
+// FP64-field model (host emulation of the exact arithmetic): product, and a chain of mixed additions
+void h_fe64_mul(uint8_t *o, const uint8_t *a, const uint8_t *b)
+{
+    fe x, y, z; load(x, a); load(y, b);
+    fe64 X, Y, Z; fe64_from_fe(X, x); fe64_from_fe(Y, y);
+    fe64_mul(Z, X, Y); fe64_mul(Z, Z, Y);
+    fe64 S; fe64_add(S, Z, X); fe64_sub(S, S, Y); fe64_mul(Z, S, X);      // (a b^2 + a - b) a
+    fe64_to_fe(z, Z); store(o, z);
+}
+// acc = sum_k (+/-) Q_k over `count` compressed points, alternating through madd / padd; returns compress(acc)
+int h_ge64_chain(uint8_t *out, const uint8_t *pts, const uint8_t *negs, int count)
+{
+    ge64_p3 acc; ge64_identity(acc);
+    for (int k = 0; k < count; k++) {
+        ge_p3 q; if (!load_point(q, pts + 32 * k)) return 0;
+        if (k & 1) {
+            ge_niels n; ge_affine_to_niels(n, q.X, q.Y);
+            ge_niels_packed pk; ge_niels_pack(pk, n);
+            ge64_niels n64; ge64_niels_unpack(n64, pk);
+            ge64_madd(acc, acc, n64, negs[k]);
+        } else {
+            ge_p3 q3; ge_dbl(q3, q); ge_add(q3, q3, q);                    // 3q, Z != 1
+            ge_pniels n; ge_p3_to_pniels(n, q3);
+            ge_pniels_packed pk; ge_pniels_pack(pk, n);
+            ge64_pniels n64; ge64_pniels_unpack(n64, pk);
+            ge64_padd(acc, acc, n64, negs[k]);
+        }
+    }
+    ge_p3 r; ge64_to_p3(r, acc);
+    store_point(out, r);
+    return 1;
+}
+}

@@ -141,3 +141,31 @@ def test_ristretto_encode_decode(host, oracle, kat):
         if P is not None:
             assert bytes(o1) == e
             assert bytes(o2) == oracle.ristretto_compress(oracle.add(oracle.double(P), P))
+
+
+def test_fe64_model(host, oracle):
+    """Host model of the FP64-pipe field (fe64.cuh): exact-product arithmetic, balanced carries and the
+    operand rule (asserted inside), against big integers and the oracle."""
+    rnd = random.Random(10)
+    p = pyref.p
+    vals = EDGE + [rnd.randrange(2**255) for _ in range(200)]
+    for i, x in enumerate(vals):
+        y = vals[(i * 5 + 1) % len(vals)]
+        assert call(host.h_fe64_mul, b32(x), b32(y)) == (x * y * y + x - y) * x % p
+    B = oracle.basepoint()
+    ident = oracle.compress(oracle.identity())
+    for trial in range(6):
+        n = 40
+        pts = [oracle.compress(oracle.scalarmul(b32(rnd.randrange(pyref.L)), B)) for _ in range(n)]
+        if trial == 0:
+            pts[3] = ident; pts[4] = b32(0); pts[5] = b32(p - 1)
+        negs = bytes(rnd.randrange(2) for _ in range(n))
+        out = (C.c_uint8 * 32)()
+        assert host.h_ge64_chain(out, b"".join(pts), negs, n) == 1
+        acc = oracle.identity()
+        for k in range(n):
+            q = oracle.decompress(pts[k])
+            if k % 2 == 0:
+                q = oracle.add(oracle.double(q), q)
+            acc = oracle.sub(acc, q) if negs[k] else oracle.add(acc, q)
+        assert bytes(out) == oracle.compress(acc)
