@@ -36,6 +36,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 L_ORDER = 2**252 + 27742317777372353535851937790883648493
 SEED = 0xDA1EC00000000001
 IMAD_WIDE_PEAK_PER_S = 8.96e12      # measured on this pool's B200, profiles/microbench_r1.json
+FIELD_MUL_PEAK_PER_S = 119e9        # field multiplications/s of the FP64-pipe field in isolation, profiles/microbench_f64_r1.json
+FIELD_MUL_PEAK_INT_PER_S = 71e9     # same for the IMAD.WIDE field (fe.cuh), profiles/microbench_r1.json
 
 
 # ------------------------------------------------------------------------------------------ utils
@@ -265,7 +267,12 @@ def run_msm(args, rank, world, local):
         achieved = algo_bytes / (kms * 1e-3) / 1e9
         c = eng_window_bits(n_total)
         adds = n_local * ((253 + c - 1) // c)
-        imad_wide = adds * 8 * 100           # 8M per projective-Niels add, 100 IMAD.WIDE per field mul
+        field_muls = adds * 8                # 8M per projective-Niels addition (curve_models.rs:411-430 + :365-372)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("k_bucket_accumulate_msm_2p20_bytes")
         line = {
             "metric": "Pippenger MSM points/sec", "value": n_total * args.steps / elapsed, "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
@@ -280,14 +287,17 @@ def run_msm(args, rank, world, local):
                     "h2d_bytes_per_step": n_local * 192, "d2h_bytes_per_step": 192 if world == 1 else nwin * 160 + 192},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_bucket_accumulate", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
                          "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)", "kernel_ms": kms,
-                         "note": "integer-multiply bound, see roofline_imad"},
-            "roofline_imad": {"bound": "IMAD.WIDE.U32 issue", "achieved": imad_wide / (kms * 1e-3) / 1e12,
-                              "peak": IMAD_WIDE_PEAK_PER_S / 1e12, "unit": "T IMAD.WIDE/s",
-                              "frac": imad_wide / (kms * 1e-3) / IMAD_WIDE_PEAK_PER_S,
-                              "peak_source": "measured microbenchmark, profiles/microbench_r1.json",
-                              "algorithmic_ops_per_launch": imad_wide},
+                         "algorithmic_bytes_per_launch": algo_bytes,
+                         "note": "arithmetic-bound, not HBM-bound: see roofline_fieldmul"},
+            "roofline_fieldmul": {"bound": "exact GF(2^255-19) multiplications (FP64 DFMA + integer pipes)",
+                                  "achieved": field_muls / (kms * 1e-3) / 1e9, "peak": FIELD_MUL_PEAK_PER_S / 1e9,
+                                  "unit": "G field mul/s", "frac": field_muls / (kms * 1e-3) / FIELD_MUL_PEAK_PER_S,
+                                  "peak_source": "register-resident multiplication chain of the same field code, measured "
+                                                 "(profiles/microbench_f64_r1.json; the IMAD.WIDE form peaks at %.0f G/s, "
+                                                 "IMAD.WIDE.U32 itself at %.2f T/s)" % (FIELD_MUL_PEAK_INT_PER_S / 1e9, IMAD_WIDE_PEAK_PER_S / 1e12),
+                                  "algorithmic_field_muls_per_launch": field_muls},
             "clocks": clocks,
         }
     return line, eng, (rank, world, local)

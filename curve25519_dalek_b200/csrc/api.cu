@@ -27,6 +27,7 @@ int dalek_b200_init(int device, dalek_b200_ctx **out)
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);       // (greatest priority is the lower number)
     if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
@@ -51,13 +52,13 @@ void dalek_b200_destroy(dalek_b200_ctx *ctx)
     DevBuf *bufs[] = {&ctx->scalars, &ctx->points_in, &ctx->points, &ctx->digits, &ctx->counts, &ctx->offsets,
                       &ctx->sorted, &ctx->buckets, &ctx->red_a, &ctx->red_b, &ctx->red_c, &ctx->red_d,
                       &ctx->result, &ctx->flags, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->misc3,
-                      &ctx->misc4, &ctx->misc5, &ctx->zs, &ctx->base_table, &ctx->ntasks, &ctx->task_off, &ctx->tasks, &ctx->task_sums};
+                      &ctx->misc4, &ctx->misc5, &ctx->zs, &ctx->base_table, &ctx->ntasks, &ctx->task_off, &ctx->tasks, &ctx->task_sums, &ctx->msg_offs};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     cudaEventDestroy(ctx->ev_join2);
     for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev_grp[i]);
-    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2);
+    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2); cudaStreamDestroy(ctx->stream_copy);
     delete ctx;
 }
 
@@ -67,7 +68,8 @@ int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value)
 {
     if (!ctx || !name) return DALEK_E_INVALID_ARG;
     if (!strcmp(name, "window_bits")) { if (value != 0 && (value < 4 || value > 20)) return DALEK_E_INVALID_ARG; ctx->opt_window_bits = value; return 0; }
-    if (!strcmp(name, "window_groups")) { if (value < 1 || value > 4) return DALEK_E_INVALID_ARG; ctx->opt_window_groups = value; return 0; }
+    if (!strcmp(name, "host_chunks")) { if (value < 1 || value > 4) return DALEK_E_INVALID_ARG; ctx->opt_host_chunks = value; return 0; }
+    if (!strcmp(name, "verify_pieces")) { if (value < 1 || value > 4) return DALEK_E_INVALID_ARG; ctx->opt_verify_pieces = value; return 0; }
     if (!strcmp(name, "field_f64")) { ctx->opt_field_f64 = value ? 1 : 0; return 0; }
     if (!strcmp(name, "verify_chunk")) { if (value < 1 || value > (1 << 20)) return DALEK_E_INVALID_ARG; ctx->opt_verify_chunk = value; return 0; }
     return DALEK_E_INVALID_ARG;
@@ -89,22 +91,48 @@ int dalek_b200_last_kernel_ms(const dalek_b200_ctx *ctx, float *ms, int *launche
 static size_t point_in_bytes(int fmt) { return fmt == DALEK_POINTS_COMPRESSED ? 32 : 160; }
 
 // device scalars/points -> window sums in ctx->red? -> result.  Returns reference-level code.
-static int run_msm_dev(dalek_b200_ctx *ctx, const void *d_scalars, const void *d_points_in, int point_fmt, size_t n,
-                       size_t n_total, ge_p3_raw *d_windows, int *bad_out, MsmResult *d_result = nullptr)
+// Inputs (host or device) -> bucket sums -> window accumulators (-> result if d_result).
+// Host inputs are streamed in chunks on a dedicated copy stream: while chunk k+1 crosses PCIe,
+// chunk k is converted, sorted and added into the (persistent) bucket sums.
+static int run_msm(dalek_b200_ctx *ctx, const void *scalars, const void *points_in, bool on_device, int point_fmt, size_t n,
+                   size_t n_total, ge_p3_raw *d_windows, int *bad_out, MsmResult *d_result)
 {
     int rc;
     const int kind = point_fmt == DALEK_POINTS_COMPRESSED ? PK_NIELS : PK_PNIELS;
     const size_t psz = kind == PK_NIELS ? sizeof(ge_niels_packed) : sizeof(ge_pniels_packed);
+    const size_t pin = point_in_bytes(point_fmt);
+    cudaStream_t st = ctx->stream;
     if ((rc = ws_reserve(ctx, ctx->points, std::max<size_t>(1, n) * psz))) return rc;
     if ((rc = ws_reserve(ctx, ctx->flags, 64))) return rc;
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->flags.p, 0, 64, ctx->stream));
-    if ((rc = msm_prepare_points(ctx, d_points_in, point_fmt, n, ctx->points.p, (int *)ctx->flags.p))) return rc;
-    int c = msm_choose_window_bits(ctx, n_total);
-    if (d_result) { if ((rc = msm_full(ctx, (const uint32_t *)d_scalars, ctx->points.p, kind, n, c, d_windows, d_result))) return rc; }
-    else if ((rc = msm_window_sums(ctx, (const uint32_t *)d_scalars, ctx->points.p, kind, n, c, d_windows))) return rc;
-    if (bad_out) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(bad_out, ctx->flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->flags.p, 0, 64, st));
+    const int c = msm_choose_window_bits(ctx, n_total);
+    if (on_device) {
+        if ((rc = msm_prepare_points(ctx, points_in, point_fmt, n, ctx->points.p, (int *)ctx->flags.p))) return rc;
+        if ((rc = msm_accumulate_chunk(ctx, (const uint32_t *)scalars, ctx->points.p, kind, n, c, true))) return rc;
+    } else {
+        if ((rc = ws_reserve(ctx, ctx->scalars, std::max<size_t>(1, n) * 32))) return rc;
+        if ((rc = ws_reserve(ctx, ctx->points_in, std::max<size_t>(1, n) * pin))) return rc;
+        int K = n >= (1u << 18) ? (int)std::min<long>(4, std::max<long>(1, ctx->opt_host_chunks)) : 1;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_copy, ctx->ev_fork, 0));
+        // equal pieces; more than two pieces do not pay: every piece re-runs the per-bucket passes
+        // (scans, task lists) and revisits all bucket sums (profiles/sweep_r1.txt)
+        for (int k = 0; k < K; k++) {
+            const size_t i0 = n * k / K, i1 = n * (k + 1) / K, cnt = i1 - i0;
+            char *ds = (char *)ctx->scalars.p + i0 * 32, *dp = (char *)ctx->points_in.p + i0 * pin;
+            if (cnt) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(ds, (const char *)scalars + i0 * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->stream_copy));
+                CUDA_TRY(ctx, cudaMemcpyAsync(dp, (const char *)points_in + i0 * pin, cnt * pin, cudaMemcpyHostToDevice, ctx->stream_copy));
+            }
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_grp[k], ctx->stream_copy));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_grp[k], 0));
+            char *dq = (char *)ctx->points.p + i0 * psz;
+            if ((rc = msm_prepare_points(ctx, dp, point_fmt, cnt, dq, (int *)ctx->flags.p))) return rc;
+            if ((rc = msm_accumulate_chunk(ctx, (const uint32_t *)ds, dq, kind, cnt, c, k == 0))) return rc;
+        }
     }
+    if ((rc = msm_reduce_finish(ctx, c, d_windows, d_result))) return rc;
+    if (bad_out) CUDA_TRY(ctx, cudaMemcpyAsync(bad_out, ctx->flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     return 0;
 }
 
@@ -136,16 +164,6 @@ static int msm_common(dalek_b200_ctx *ctx, const void *scalars, const void *poin
     if (n >= (1ull << 31)) return DALEK_E_INVALID_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     int rc;
-    const void *d_s = scalars, *d_p = points;
-    if (!on_device) {
-        if ((rc = ws_reserve(ctx, ctx->scalars, std::max<size_t>(1, n) * 32))) return rc;
-        if ((rc = ws_reserve(ctx, ctx->points_in, std::max<size_t>(1, n) * point_in_bytes(point_fmt)))) return rc;
-        if (n) {
-            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->points_in.p, points, n * point_in_bytes(point_fmt), cudaMemcpyHostToDevice, ctx->stream));
-        }
-        d_s = ctx->scalars.p; d_p = ctx->points_in.p;
-    }
     int c = msm_choose_window_bits(ctx, n);
     int nwin = msm_window_count_for_bits(c);
     if ((rc = ws_reserve(ctx, ctx->misc0, (size_t)nwin * sizeof(ge_p3_raw)))) return rc;
@@ -153,7 +171,7 @@ static int msm_common(dalek_b200_ctx *ctx, const void *scalars, const void *poin
     int *h_bad = (int *)((char *)ctx->h_pinned + sizeof(MsmResult));
     *h_bad = 0;
     if ((rc = ws_reserve(ctx, ctx->result, sizeof(MsmResult)))) return rc;
-    if ((rc = run_msm_dev(ctx, d_s, d_p, point_fmt, n, n, (ge_p3_raw *)ctx->misc0.p, h_bad, (MsmResult *)ctx->result.p))) return rc;
+    if ((rc = run_msm(ctx, scalars, points, on_device, point_fmt, n, n, (ge_p3_raw *)ctx->misc0.p, h_bad, (MsmResult *)ctx->result.p))) return rc;
     if ((rc = finish_msm(ctx, (const ge_p3_raw *)ctx->misc0.p, 1, n, out_compressed, out_limbs, nullptr, true))) return rc;
     return *h_bad ? DALEK_NONE : DALEK_OK;
 }
@@ -222,16 +240,6 @@ static int partial_common(dalek_b200_ctx *ctx, const void *scalars, const void *
         return DALEK_E_INVALID_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     int rc;
-    const void *d_s = scalars, *d_p = points;
-    if (!on_device) {
-        if ((rc = ws_reserve(ctx, ctx->scalars, std::max<size_t>(1, n_local) * 32))) return rc;
-        if ((rc = ws_reserve(ctx, ctx->points_in, std::max<size_t>(1, n_local) * point_in_bytes(point_fmt)))) return rc;
-        if (n_local) {
-            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n_local * 32, cudaMemcpyHostToDevice, ctx->stream));
-            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->points_in.p, points, n_local * point_in_bytes(point_fmt), cudaMemcpyHostToDevice, ctx->stream));
-        }
-        d_s = ctx->scalars.p; d_p = ctx->points_in.p;
-    }
     int c = msm_choose_window_bits(ctx, n_total);
     int nwin = msm_window_count_for_bits(c);
     if ((rc = ws_reserve(ctx, ctx->misc0, (size_t)nwin * sizeof(ge_p3_raw)))) return rc;
@@ -239,7 +247,7 @@ static int partial_common(dalek_b200_ctx *ctx, const void *scalars, const void *
     if ((rc = pinned_reserve(ctx, (size_t)nwin * 160 + 64))) return rc;
     int *h_bad = (int *)((char *)ctx->h_pinned + (size_t)nwin * 160);
     *h_bad = 0;
-    if ((rc = run_msm_dev(ctx, d_s, d_p, point_fmt, n_local, n_total, (ge_p3_raw *)ctx->misc0.p, h_bad))) return rc;
+    if ((rc = run_msm(ctx, scalars, points, on_device, point_fmt, n_local, n_total, (ge_p3_raw *)ctx->misc0.p, h_bad, nullptr))) return rc;
     k_windows_to_limbs<<<(nwin + 63) / 64, 64, 0, ctx->stream>>>((const ge_p3_raw *)ctx->misc0.p, nwin, (uint64_t *)ctx->misc1.p);
     ctx->launches++;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->misc1.p, (size_t)nwin * 160, cudaMemcpyDeviceToHost, ctx->stream));

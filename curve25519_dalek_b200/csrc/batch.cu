@@ -95,10 +95,11 @@ k_transcript(const uint32_t *__restrict__ hrams, const uint32_t *__restrict__ si
     }
 }
 
-// scalars[0] is written by k_sum_final; scalars[1+i] = z_i; scalars[1+n+i] = z_i h_i; zs_prod[i] = z_i s_i
+// out_z[i] = z_i, out_zh[i] = z_i h_i (slots 1+i and 1+n+i of the MSM scalar array; slot 0 is written by
+// k_sum_final); zs_prod[i] = z_i s_i
 __global__ void __launch_bounds__(128)
 k_coeffs(const uint32_t *__restrict__ zs, const uint32_t *__restrict__ sigs, const uint32_t *__restrict__ hs, size_t n,
-         uint32_t *__restrict__ scalars, uint32_t *__restrict__ zs_prod)
+         uint32_t *__restrict__ out_z, uint32_t *__restrict__ out_zh, uint32_t *__restrict__ zs_prod)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -108,10 +109,10 @@ k_coeffs(const uint32_t *__restrict__ zs, const uint32_t *__restrict__ sigs, con
 #pragma unroll
     for (int k = 0; k < 8; k++) { s[k] = sigs[16 * i + 8 + k]; h[k] = hs[8 * i + k]; }
 #pragma unroll
-    for (int k = 0; k < 8; k++) scalars[8 * (1 + i) + k] = z[k];
+    for (int k = 0; k < 8; k++) out_z[8 * i + k] = z[k];
     sc_mul(r, z, h);
 #pragma unroll
-    for (int k = 0; k < 8; k++) scalars[8 * (1 + n + i) + k] = r[k];
+    for (int k = 0; k < 8; k++) out_zh[8 * i + k] = r[k];
     sc_mul(r, z, s);
 #pragma unroll
     for (int k = 0; k < 8; k++) zs_prod[8 * i + k] = r[k];
@@ -169,20 +170,25 @@ __global__ void k_sum_final(const uint32_t *__restrict__ partial, uint32_t count
     }
 }
 
-// decompress R_i (stride 64 B inside the signature) and A_i into the point array; slot 0 = basepoint
+// decompress R_i (first half of each signature) and A_i of `cnt` signatures into their slots of the
+// MSM point array (out_R = &points[1 + i0], out_A = &points[1 + n + i0]); out_B (slot 0) gets the basepoint
 __global__ void __launch_bounds__(128)
-k_prep_RA(const uint32_t *__restrict__ sigs, const uint32_t *__restrict__ keys, size_t n,
-          ge_niels_packed *__restrict__ points, int *__restrict__ flags)
+k_prep_RA(const uint32_t *__restrict__ sigs, const uint32_t *__restrict__ keys, size_t cnt,
+          ge_niels_packed *__restrict__ out_R, ge_niels_packed *__restrict__ out_A, ge_niels_packed *__restrict__ out_B,
+          int *__restrict__ flags)
 {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j > 2 * n) return;
+    if (j > 2 * cnt || (j == 2 * cnt && !out_B)) return;
     fe x, y;
-    if (j == 0) {
+    ge_niels_packed *dst;
+    if (j == 2 * cnt) {
         fe_const_base_x(x); fe_const_base_y(y);
+        dst = out_B;
     } else {
         uint32_t s[8];
-        bool isR = j <= n;
-        const uint32_t *src = isR ? sigs + 16 * (j - 1) : keys + 8 * (j - 1 - n);
+        bool isR = j < cnt;
+        const uint32_t *src = isR ? sigs + 16 * j : keys + 8 * (j - cnt);
+        dst = isR ? out_R + j : out_A + (j - cnt);
 #pragma unroll
         for (int k = 0; k < 8; k++) s[k] = src[k];
         if (!ge_decompress_affine(x, y, s)) {
@@ -192,20 +198,19 @@ k_prep_RA(const uint32_t *__restrict__ sigs, const uint32_t *__restrict__ keys, 
     }
     ge_niels nl; ge_affine_to_niels(nl, x, y);
     ge_niels_packed p; ge_niels_pack(p, nl);
-    uint4 *o = reinterpret_cast<uint4 *>(points + j);
+    uint4 *o = reinterpret_cast<uint4 *>(dst);
 #pragma unroll
     for (int k = 0; k < 6; k++) o[k] = make_uint4(p.w[4 * k], p.w[4 * k + 1], p.w[4 * k + 2], p.w[4 * k + 3]);
 }
 
 // ------------------------------------------------------------------------------------------
-static int verify_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t *d_offs, const uint32_t *d_sigs,
-                      const uint32_t *d_keys, size_t n)
+struct VerifyBufs { uint32_t *hrams, *hs, *zsprod, *zs, *scalars; ge_niels_packed *points; int *flags; };
+
+static int verify_reserve(dalek_b200_ctx *ctx, size_t n, VerifyBufs &b)
 {
     int rc;
-    cudaStream_t st = ctx->stream, st2 = ctx->stream2;
     const size_t m = 2 * n + 1;
     if (m >= (1ull << 31)) return DALEK_E_INVALID_ARG;
-    uint32_t chunk = (uint32_t)ctx->opt_verify_chunk;
     if ((rc = ws_reserve(ctx, ctx->misc2, std::max<size_t>(1, n) * 64))) return rc;   // hrams
     if ((rc = ws_reserve(ctx, ctx->misc3, std::max<size_t>(1, n) * 32))) return rc;   // h_i
     if ((rc = ws_reserve(ctx, ctx->misc4, std::max<size_t>(1, n) * 32))) return rc;   // z_i s_i
@@ -213,48 +218,65 @@ static int verify_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t
     if ((rc = ws_reserve(ctx, ctx->scalars, m * 32))) return rc;
     if ((rc = ws_reserve(ctx, ctx->points, m * sizeof(ge_niels_packed)))) return rc;
     if ((rc = ws_reserve(ctx, ctx->flags, 64))) return rc;
-    const uint32_t nsum = 32768;
-    if ((rc = ws_reserve(ctx, ctx->misc5, (size_t)nsum * 9 * 4))) return rc;
-    int *flags = (int *)ctx->flags.p;
-    uint32_t *scalars = (uint32_t *)ctx->scalars.p;
-    CUDA_TRY(ctx, cudaMemsetAsync(flags, 0, 64, st));
-    // Two streams: the hashing -> transcript -> coefficient chain (a long dependency chain with little
-    // parallelism in the transcript) is enqueued first on the high-priority stream; decompression
-    // (plenty of independent work, bound by the integer-multiply pipe) fills the machine from the
-    // second stream while the sponges run.
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
-    if (n) {
-        k_hram<<<cdiv(n, 128), 128, 0, st>>>(d_msgs, d_offs, d_sigs, d_keys, n, (uint32_t *)ctx->misc2.p,
-                                             (uint32_t *)ctx->misc3.p, flags);
-        size_t nchunks = (n + chunk - 1) / chunk;
-        k_transcript<<<cdiv(nchunks, 64), 64, 0, st>>>((const uint32_t *)ctx->misc2.p, d_sigs, n, chunk, (uint32_t *)ctx->zs.p);
+    if ((rc = ws_reserve(ctx, ctx->misc5, (size_t)32768 * 9 * 4))) return rc;
+    b.hrams = (uint32_t *)ctx->misc2.p; b.hs = (uint32_t *)ctx->misc3.p; b.zsprod = (uint32_t *)ctx->misc4.p;
+    b.zs = (uint32_t *)ctx->zs.p; b.scalars = (uint32_t *)ctx->scalars.p; b.points = (ge_niels_packed *)ctx->points.p;
+    b.flags = (int *)ctx->flags.p;
+    return 0;
+}
+
+// Front end for signatures [i0, i1) (i0 a multiple of verify_chunk): hashing, transcript, coefficients on
+// the main (high-priority) stream; decompression on the second stream.  Both wait for `ready` if given.
+static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t *d_msgs, const uint64_t *d_offs,
+                        const uint32_t *d_sigs, const uint32_t *d_keys, size_t n, size_t i0, size_t i1, cudaEvent_t ready)
+{
+    cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+    const size_t cnt = i1 - i0;
+    const uint32_t chunk = (uint32_t)ctx->opt_verify_chunk;
+    if (ready) { CUDA_TRY(ctx, cudaStreamWaitEvent(st, ready, 0)); CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ready, 0)); }
+    if (cnt) {
+        // the hashing -> transcript chain has little parallelism in its second stage: enqueue it first
+        k_hram<<<cdiv(cnt, 128), 128, 0, st>>>(d_msgs, d_offs + i0, d_sigs + 16 * i0, d_keys + 8 * i0, cnt, b.hrams + 16 * i0,
+                                               b.hs + 8 * i0, b.flags);
+        size_t nchunks = (cnt + chunk - 1) / chunk;
+        k_transcript<<<cdiv(nchunks, 64), 64, 0, st>>>(b.hrams + 16 * i0, d_sigs + 16 * i0, cnt, chunk, b.zs + 4 * i0);
         ctx->launches += 2;
     }
-    CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
-    k_prep_RA<<<cdiv(m, 128), 128, 0, st2>>>(d_sigs, d_keys, n, (ge_niels_packed *)ctx->points.p, flags);
+    k_prep_RA<<<cdiv(2 * cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, d_keys + 8 * i0, cnt, b.points + 1 + i0, b.points + 1 + n + i0,
+                                                       i0 == 0 ? b.points : nullptr, b.flags);
     ctx->launches++;
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, st2));
-    if (n) {
-        k_coeffs<<<cdiv(n, 128), 128, 0, st>>>((const uint32_t *)ctx->zs.p, d_sigs, (const uint32_t *)ctx->misc3.p, n,
-                                               scalars, (uint32_t *)ctx->misc4.p);
+    if (cnt) {
+        k_coeffs<<<cdiv(cnt, 128), 128, 0, st>>>(b.zs + 4 * i0, d_sigs + 16 * i0, b.hs + 8 * i0, cnt, b.scalars + 8 * (1 + i0),
+                                                 b.scalars + 8 * (1 + n + i0), b.zsprod + 8 * i0);
         ctx->launches++;
     }
-    k_sum_partial<<<cdiv(nsum, 128), 128, 0, st>>>((const uint32_t *)ctx->misc4.p, n, nsum, (uint32_t *)ctx->misc5.p);
-    k_sum_final<<<1, 256, 0, st>>>((const uint32_t *)ctx->misc5.p, nsum, scalars);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+// -sum z_i s_i, the (2n+1)-term MSM (batch.rs:240-244) and the verdict
+static int verify_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n)
+{
+    int rc;
+    cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+    const size_t m = 2 * n + 1;
+    const uint32_t nsum = 32768;
+    k_sum_partial<<<cdiv(nsum, 128), 128, 0, st>>>(b.zsprod, n, nsum, (uint32_t *)ctx->misc5.p);
+    k_sum_final<<<1, 256, 0, st>>>((const uint32_t *)ctx->misc5.p, nsum, b.scalars);
     ctx->launches += 2;
     ctx->last_zs_n = n;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, st2));
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
-    // the (2n+1)-term MSM (batch.rs:240-244)
     int c = msm_choose_window_bits(ctx, m);
     int nwin = msm_window_count_for_bits(c);
     if ((rc = ws_reserve(ctx, ctx->misc0, (size_t)nwin * sizeof(ge_p3_raw)))) return rc;
     if ((rc = ws_reserve(ctx, ctx->result, sizeof(MsmResult)))) return rc;
-    if ((rc = msm_full(ctx, scalars, ctx->points.p, PK_NIELS, m, c, (ge_p3_raw *)ctx->misc0.p, (MsmResult *)ctx->result.p))) return rc;
+    if ((rc = msm_full(ctx, b.scalars, b.points, PK_NIELS, m, c, (ge_p3_raw *)ctx->misc0.p, (MsmResult *)ctx->result.p))) return rc;
     if ((rc = pinned_reserve(ctx, sizeof(MsmResult) + 128))) return rc;
     MsmResult *h = (MsmResult *)ctx->h_pinned;
     int *hflags = (int *)((char *)ctx->h_pinned + sizeof(MsmResult));
     CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->result.p, sizeof(MsmResult), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(hflags, b.flags, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
@@ -264,6 +286,18 @@ static int verify_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t
     if (hflags[FLAG_BAD_S]) return ED25519_ERR_SCALAR_FORMAT;
     if (hflags[FLAG_BAD_R]) return ED25519_ERR_VERIFY;
     return h->is_identity ? DALEK_OK : ED25519_ERR_VERIFY;
+}
+
+static int verify_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t *d_offs, const uint32_t *d_sigs,
+                      const uint32_t *d_keys, size_t n)
+{
+    int rc;
+    VerifyBufs b;
+    if ((rc = verify_reserve(ctx, n, b))) return rc;
+    CUDA_TRY(ctx, cudaMemsetAsync(b.flags, 0, 64, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    if ((rc = verify_front(ctx, b, d_msgs, d_offs, d_sigs, d_keys, n, 0, n, ctx->ev_fork))) return rc;
+    return verify_tail(ctx, b, n);
 }
 
 extern "C" {
@@ -287,19 +321,36 @@ int ed25519_b200_verify_batch_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat
     size_t mbytes = n ? (size_t)msg_offsets[n] : 0;
     if (n && msg_offsets[0] != 0) return DALEK_E_INVALID_ARG;
     if ((rc = ws_reserve(ctx, ctx->misc1, mbytes + 16))) return rc;
-    if ((rc = ws_reserve(ctx, ctx->red_a, (n + 1) * 8))) return rc;          // offsets (reduction scratch is idle here)
+    if ((rc = ws_reserve(ctx, ctx->msg_offs, (n + 1) * 8))) return rc;
     if ((rc = ws_reserve(ctx, ctx->points_in, std::max<size_t>(1, n) * 96))) return rc;   // sigs + keys
-    uint8_t *d_sigs = (uint8_t *)ctx->points_in.p, *d_keys = d_sigs + n * 64;
-    if (n) {
-        if (mbytes) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->misc1.p, msgs_flat, mbytes, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->red_a.p, msg_offsets, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_sigs, sigs, n * 64, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_keys, pubkeys, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    VerifyBufs b;
+    if ((rc = verify_reserve(ctx, n, b))) return rc;
+    uint8_t *d_msgs = (uint8_t *)ctx->misc1.p, *d_sigs = (uint8_t *)ctx->points_in.p, *d_keys = d_sigs + n * 64;
+    uint64_t *d_offs = (uint64_t *)ctx->msg_offs.p;
+    cudaStream_t st = ctx->stream, sc = ctx->stream_copy;
+    CUDA_TRY(ctx, cudaMemsetAsync(b.flags, 0, 64, st));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(sc, ctx->ev_fork, 0));
+    // stream the batch in up to 4 pieces (boundaries on verify_chunk multiples): the copy of piece k+1
+    // overlaps hashing / decompression of piece k
+    const size_t vc = (size_t)ctx->opt_verify_chunk;
+    int K = n >= (1u << 18) ? (int)std::min<long>(4, std::max<long>(1, ctx->opt_verify_pieces)) : 1;
+    size_t prev = 0;
+    for (int k = 0; k < K; k++) {
+        size_t i1 = k == K - 1 ? n : std::min(n, ((n * (k + 1) / K) / vc) * vc);     // equal pieces: the front end outlasts the copies
+        size_t i0 = prev, cnt = i1 - i0;
+        prev = i1;
+        if (cnt) {
+            size_t m0 = (size_t)msg_offsets[i0], m1 = (size_t)msg_offsets[i1];
+            if (m1 > m0) CUDA_TRY(ctx, cudaMemcpyAsync(d_msgs + m0, msgs_flat + m0, m1 - m0, cudaMemcpyHostToDevice, sc));
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_offs + i0, msg_offsets + i0, (cnt + 1) * 8, cudaMemcpyHostToDevice, sc));
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_sigs + i0 * 64, sigs + i0 * 64, cnt * 64, cudaMemcpyHostToDevice, sc));
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_keys + i0 * 32, pubkeys + i0 * 32, cnt * 32, cudaMemcpyHostToDevice, sc));
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_grp[k], sc));
+        if ((rc = verify_front(ctx, b, d_msgs, d_offs, (const uint32_t *)d_sigs, (const uint32_t *)d_keys, n, i0, i1, ctx->ev_grp[k]))) return rc;
     }
-    // red_a is reused by the MSM reduction later in the same stream; the offsets are only read by
-    // k_hram, which is ordered before it.
-    return verify_dev(ctx, (const uint8_t *)ctx->misc1.p, (const uint64_t *)ctx->red_a.p, (const uint32_t *)d_sigs,
-                      (const uint32_t *)d_keys, n);
+    return verify_tail(ctx, b, n);
 }
 
 int ed25519_b200_verify_batch(dalek_b200_ctx *ctx, const uint8_t *const *msgs, const size_t *msg_lens,

@@ -19,6 +19,7 @@ struct dalek_b200_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;
+    cudaStream_t stream_copy = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     cudaEvent_t ev_grp[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string last_error;
@@ -26,14 +27,15 @@ struct dalek_b200_ctx {
     // options
     long opt_window_bits = 0;
     long opt_verify_chunk = 128;
-    long opt_window_groups = 1; // >1: window groups pipelined over two streams (measured slower on B200: profiles/sweep_r1.txt)
+    long opt_host_chunks = 2;   // host-buffer MSM calls stream the pairs in this many chunks (copy/compute overlap)
+    long opt_verify_pieces = 4; // host-buffer verify_batch calls stream the signatures in this many pieces
     long opt_field_f64 = 1;     // bucket kernel on the FP64 pipe (fe64.cuh) instead of IMAD.WIDE (fe.cuh)
     // timing of the dominant kernel in the last call
     float last_kernel_ms = 0.f;
     int last_kernel_launches = 0;
     // device workspaces (grown on demand, reused across calls)
     DevBuf scalars, points_in, points, digits, counts, offsets, sorted, buckets, red_a, red_b, red_c,
-        red_d, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums;
+        red_d, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums, msg_offs;
     bool base_table_ready = false;
     // pinned host staging
     void *h_pinned = nullptr;
@@ -73,7 +75,11 @@ int msm_window_sums(dalek_b200_ctx *ctx, const uint32_t *d_scalars /* n x 8 word
 // total = sum over ranks of windows, Horner-combined; writes compressed (8 words) + canonical
 // limbs51 (20 u64) + identity flag to d_result (layout: 8 u32 | pad | 20 u64 | u32 flag).
 struct MsmResult { uint32_t compressed[8]; uint64_t limbs[20]; uint32_t is_identity; uint32_t pad; };
-// window sums + pipelined Horner + encode in one go (single-shard case)
+// building blocks: one chunk of pairs into the buckets; then reduction (+ Horner + encode if d_result)
+int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n,
+                         int c, bool first);
+int msm_reduce_finish(dalek_b200_ctx *ctx, int c, ge_p3_raw *d_windows, MsmResult *d_result);
+// window sums + Horner + encode in one go (single-shard case)
 int msm_full(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n, int c,
              ge_p3_raw *d_windows, MsmResult *d_result);
 int msm_combine_windows(dalek_b200_ctx *ctx, const ge_p3_raw *d_windows, int ranks, int nwin, int c,

@@ -269,13 +269,22 @@ __global__ void k_task_fill(const uint32_t *__restrict__ ntasks, const uint32_t 
     for (uint32_t j = 0; j < k; j++) tasks[base + j] = make_uint2(t, j);
 }
 
+__device__ __forceinline__ void load_p3(ge_p3 &p, const ge_p3_raw *src)
+{
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    ge_p3_raw r;
+#pragma unroll
+    for (int q = 0; q < 10; q++) { uint4 v = s[q]; r.w[4 * q] = v.x; r.w[4 * q + 1] = v.y; r.w[4 * q + 2] = v.z; r.w[4 * q + 3] = v.w; }
+    ge_p3_load_raw(p, r);
+}
+
 template <int KIND, int F64>
 __global__ void __launch_bounds__(128, ACC_MIN_BLOCKS)
 k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict__ sorted,
                     const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets,
                     const uint32_t *__restrict__ ntasks, const uint2 *__restrict__ tasks,
                     const uint32_t *__restrict__ win_base, int w0, int w1, size_t n, uint32_t nbuckets,
-                    ge_p3_raw *__restrict__ buckets, ge_p3_raw *__restrict__ task_sums)
+                    ge_p3_raw *__restrict__ buckets, ge_p3_raw *__restrict__ task_sums, int first)
 {
     __shared__ uint32_t s_key[128];     // (len << 8) | local task index, sorted descending
     __shared__ uint4 s_pts[F64 ? 2 : 1][F64 ? 8 : 1][F64 ? 128 : 1];   // prefetch slots, [buffer][piece][thread]: conflict-free
@@ -311,6 +320,12 @@ k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict_
     const uint32_t t = tk.x, w = t / nbuckets;
     const uint32_t cnt = counts[t], start = tk.y * TASK_LEN;
     const uint32_t len = min(TASK_LEN, cnt - start);
+    // `first` = first chunk of points: buckets start at the identity.  Later chunks (host inputs are
+    // streamed in chunks so that the copies overlap the arithmetic) add onto the stored bucket sums;
+    // the stored sum is folded in by piece 0 of the bucket (or by k_heavy_fixup for split buckets).
+    const bool split = ntasks[t] != 1;
+    if (!first && len == 0) return;                        // nothing new for this bucket
+    const bool fold_old = !first && !split;
     const uint32_t *idx = sorted + (size_t)w * n + offsets[t] + start;
     ge_p3 acc;
     if (F64) {
@@ -319,7 +334,13 @@ k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict_
         // slots per thread) is in flight while the current addition runs, so the HBM/L2 latency of the
         // random gathers is off the dependent path.
         constexpr int NQ = KIND == PK_NIELS ? 6 : 8;            // 16-byte pieces per point
-        ge64_p3 acc64; ge64_identity(acc64);
+        ge64_p3 acc64;
+        if (fold_old) {
+            ge_p3 old; load_p3(old, buckets + t);
+            fe64_from_fe(acc64.X, old.X); fe64_from_fe(acc64.Y, old.Y); fe64_from_fe(acc64.Z, old.Z); fe64_from_fe(acc64.T, old.T);
+        } else {
+            ge64_identity(acc64);
+        }
         uint32_t e_next = len ? idx[0] : 0;
         auto prefetch = [&](uint32_t e, int buf) {
             const uint32_t pi = e & 0x7fffffffu;
@@ -354,7 +375,7 @@ k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict_
         }
         ge64_to_p3(acc, acc64);
     } else {
-    ge_p3_identity(acc);
+    if (fold_old) load_p3(acc, buckets + t); else ge_p3_identity(acc);
     for (uint32_t k = 0; k < len; k++) {
         uint32_t e = idx[k];
         uint32_t neg = e >> 31, pi = e & 0x7fffffffu;
@@ -376,18 +397,9 @@ k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict_
     }
     }
     ge_p3_raw r; ge_p3_store_raw(r, acc);
-    uint4 *o = reinterpret_cast<uint4 *>(ntasks[t] == 1 ? buckets + t : task_sums + p);
+    uint4 *o = reinterpret_cast<uint4 *>(!split ? buckets + t : task_sums + p);
 #pragma unroll
     for (int q = 0; q < 10; q++) o[q] = make_uint4(r.w[4 * q], r.w[4 * q + 1], r.w[4 * q + 2], r.w[4 * q + 3]);
-}
-
-__device__ __forceinline__ void load_p3(ge_p3 &p, const ge_p3_raw *src)
-{
-    const uint4 *s = reinterpret_cast<const uint4 *>(src);
-    ge_p3_raw r;
-#pragma unroll
-    for (int q = 0; q < 10; q++) { uint4 v = s[q]; r.w[4 * q] = v.x; r.w[4 * q + 1] = v.y; r.w[4 * q + 2] = v.z; r.w[4 * q + 3] = v.w; }
-    ge_p3_load_raw(p, r);
 }
 
 // Everything below is latency-bound tree work on few points: it runs on groups of four lanes
@@ -398,7 +410,7 @@ __device__ __forceinline__ void load_p3(ge_p3 &p, const ge_p3_raw *src)
 __global__ void __launch_bounds__(128)
 k_heavy_fixup(const uint32_t *__restrict__ heavy, const uint32_t *__restrict__ ntasks, const uint32_t *__restrict__ task_off,
               const uint32_t *__restrict__ win_base, uint32_t nbuckets, uint32_t w0, uint32_t w1,
-              const ge_p3_raw *__restrict__ task_sums, ge_p3_raw *__restrict__ buckets)
+              const ge_p3_raw *__restrict__ task_sums, ge_p3_raw *__restrict__ buckets, int first)
 {
     const uint32_t lane = threadIdx.x & 31, role = lane & 3, grp = lane >> 2;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -409,7 +421,7 @@ k_heavy_fixup(const uint32_t *__restrict__ heavy, const uint32_t *__restrict__ n
         uint32_t kk = ntasks[tb];
         uint32_t base = win_base[tb / nbuckets] + task_off[tb];
         w4_point acc, x;
-        w4_identity(acc);
+        if (first || grp != 0) w4_identity(acc); else w4_load(acc, buckets + tb);   // later chunks: keep the old sum
         for (uint32_t j0 = 0; j0 < kk; j0 += 8) {          // uniform trip count across the warp
             uint32_t j = j0 + grp;
             if (j < kk) w4_load(x, task_sums + base + j); else w4_identity(x);
@@ -570,19 +582,20 @@ __global__ void k_encode(const ge_p3_raw *__restrict__ state, MsmResult *__restr
 }
 
 // ------------------------------------------------------------------------------------------
-// Window groups (top windows first) are pipelined over two streams: while the bucket kernel works on
-// group g+1, the reduction tree and the Horner steps of group g run on the second stream.
-static int msm_pipeline(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n,
-                        int c, ge_p3_raw *d_windows, MsmResult *d_result)
+// One chunk of (scalar, point) pairs: digits, counting sort, task lists and bucket accumulation.
+// `first` chunks start the buckets at the identity; later chunks add onto them.  All chunks of one
+// MSM must use the same window width c.
+int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n,
+                         int c, bool first)
 {
     const int nwin = msm_window_count_for_bits(c);
     const uint32_t nb = 1u << (c - 1);
     const size_t total_buckets = (size_t)nwin * nb;
     const size_t max_tasks = total_buckets + (std::max<size_t>(1, n) * nwin) / TASK_LEN + 1;
-    cudaStream_t st = ctx->stream;
-    int rc;
     const size_t max_heavy = (std::max<size_t>(1, n) * nwin) / TASK_LEN + 1;
     const uint32_t parts = (nb + SCAN_PART - 1) / SCAN_PART;
+    cudaStream_t st = ctx->stream;
+    int rc;
     // counts | heavy list (count + entries): one memset clears both
     if ((rc = ws_reserve(ctx, ctx->counts, total_buckets * 4 + (1 + max_heavy) * 4))) return rc;
     if ((rc = ws_reserve(ctx, ctx->offsets, total_buckets * 4 + (size_t)nwin * parts * 4))) return rc;
@@ -623,14 +636,34 @@ static int msm_pipeline(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const vo
         k_scatter<<<cdiv(n, 256), 256, 0, st>>>(entries, offsets, n, nwin, nb, sorted);
         ctx->launches++;
     }
-    // ---- window groups
-    int G = (int)ctx->opt_window_groups;
-    if (G < 1 || nwin < 2 * G || n < 8192) G = 1;        // tiny problems are launch-bound: do not split                                    // tiny problems are launch-bound: do not split
-    cudaStream_t sb = ctx->stream2;
-    // reduction scratch: level structure is the same for every window
+    if (first) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st));
+    {
+        const unsigned grid = cdiv(max_tasks, 128);
+        const int f = first ? 1 : 0;
+#define LAUNCH_ACC(KIND_, F64_) k_bucket_accumulate<KIND_, F64_><<<grid, 128, 0, st>>>(d_points, sorted, counts, offsets, ntasks, tasks, win_base, 0, nwin, n, nb, buckets, task_sums, f)
+        if (point_kind == PK_NIELS) { if (ctx->opt_field_f64) LAUNCH_ACC(PK_NIELS, 1); else LAUNCH_ACC(PK_NIELS, 0); }
+        else { if (ctx->opt_field_f64) LAUNCH_ACC(PK_PNIELS, 1); else LAUNCH_ACC(PK_PNIELS, 0); }
+#undef LAUNCH_ACC
+        k_heavy_fixup<<<ctx->sm_count * 4, 128, 0, st>>>(heavy, ntasks, task_off, win_base, nb, 0u, (uint32_t)nwin, task_sums, buckets, f);
+        ctx->launches += 2;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, st));          // ev_a .. ev_b brackets the accumulation kernels
+    ctx->last_kernel_launches = first ? 1 : ctx->last_kernel_launches + 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+// Bucket reduction of all windows, and (if d_result) the Horner over windows + encoding.
+int msm_reduce_finish(dalek_b200_ctx *ctx, int c, ge_p3_raw *d_windows, MsmResult *d_result)
+{
+    const int nwin = msm_window_count_for_bits(c);
+    const uint32_t nb = 1u << (c - 1);
+    cudaStream_t st = ctx->stream;
+    int rc;
+    ge_p3_raw *buckets = (ge_p3_raw *)ctx->buckets.p;
     LevelInfo li; li.nlevels = 0;
     std::vector<uint32_t> lvl_m, lvl_nout;
-    size_t pool_pts_per_win = 0;
+    size_t pool_pts = 0;
     {
         uint32_t n_in = nb; bool first = true;
         while (n_in > 1) {
@@ -639,75 +672,44 @@ static int msm_pipeline(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const vo
             lvl_m.push_back(m); lvl_nout.push_back(n_out);
             int lg = 0; while ((1u << lg) < m) lg++;
             li.log2m[li.nlevels++] = lg;
-            pool_pts_per_win += 2 * (size_t)n_out;
+            pool_pts += 2 * (size_t)n_out * nwin;
             n_in = n_out; first = false;
         }
     }
-    if ((rc = ws_reserve(ctx, ctx->red_a, std::max<size_t>(1, pool_pts_per_win * nwin) * sizeof(ge_p3_raw)))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->red_a, std::max<size_t>(1, pool_pts) * sizeof(ge_p3_raw)))) return rc;
     if ((rc = ws_reserve(ctx, ctx->red_b, (size_t)16 * nwin * sizeof(ge_p3_raw)))) return rc;
-    if ((rc = ws_reserve(ctx, ctx->red_c, sizeof(ge_p3_raw)))) return rc;
-    ge_p3_raw *pool_all = (ge_p3_raw *)ctx->red_a.p, *A_all = (ge_p3_raw *)ctx->red_b.p, *state = (ge_p3_raw *)ctx->red_c.p;
-
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st));
-    for (int g = 0; g < G; g++) {
-        const int w1 = nwin - (nwin * g) / G, w0 = nwin - (nwin * (g + 1)) / G, nwg = w1 - w0;
-        const size_t max_tasks_g = (size_t)nwg * nb + (std::max<size_t>(1, n) * nwg) / TASK_LEN + 1;
-        const unsigned grid = cdiv(max_tasks_g, 128);
-#define LAUNCH_ACC(KIND_, F64_) k_bucket_accumulate<KIND_, F64_><<<grid, 128, 0, st>>>(d_points, sorted, counts, offsets, ntasks, tasks, win_base, w0, w1, n, nb, buckets, task_sums)
-        if (point_kind == PK_NIELS) { if (ctx->opt_field_f64) LAUNCH_ACC(PK_NIELS, 1); else LAUNCH_ACC(PK_NIELS, 0); }
-        else { if (ctx->opt_field_f64) LAUNCH_ACC(PK_PNIELS, 1); else LAUNCH_ACC(PK_PNIELS, 0); }
-#undef LAUNCH_ACC
-        k_heavy_fixup<<<ctx->sm_count * 4, 128, 0, st>>>(heavy, ntasks, task_off, win_base, nb, (uint32_t)w0, (uint32_t)w1, task_sums, buckets);
-        ctx->launches += 2;
-        if (g == G - 1) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, st));   // end of the bucket-accumulation kernels
-        cudaStream_t sr = G > 1 ? sb : st;                  // where this group's tail runs
-        if (G > 1) {
-            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_grp[g], st));
-            CUDA_TRY(ctx, cudaStreamWaitEvent(sb, ctx->ev_grp[g], 0));
-        }
-        // reduction of windows [w0, w1)
-        ge_p3_raw *pool = pool_all + pool_pts_per_win * w0, *A = A_all + (size_t)16 * w0;
-        const ge_p3_raw *S_in = buckets + (size_t)w0 * nb;
-        uint32_t n_in = nb;
-        size_t pos = 0;
-        std::vector<std::pair<size_t, uint32_t>> w_arrays;
-        for (int l = 0; l < li.nlevels; l++) {
-            uint32_t m = lvl_m[l], n_out = lvl_nout[l];
-            ge_p3_raw *S_out = pool + pos, *W_out = pool + pos + (size_t)n_out * nwg;
-            k_chunk_reduce<<<cdiv((size_t)n_out * nwg * 4, 128), 128, 0, sr>>>(S_in, n_in, m, l == 0 ? 1u : 0u, n_out, nwg, S_out, W_out);
-            ctx->launches++;
-            w_arrays.push_back({pos + (size_t)n_out * nwg, n_out});
-            S_in = S_out; n_in = n_out; pos += 2 * (size_t)n_out * nwg;
-        }
-        {
-            SumArrays arrs;
-            int total = li.nlevels * nwg, done = 0;
-            while (done < total) {
-                int batch = std::min(160, total - done);
-                for (int k = 0; k < batch; k++) {
-                    int id = done + k, l = id / nwg, w = id % nwg;
-                    arrs.off[k] = (uint32_t)(w_arrays[l].first + (size_t)w * w_arrays[l].second);
-                    arrs.len[k] = w_arrays[l].second;
-                }
-                k_plain_sum<<<batch, 128, 0, sr>>>(pool, arrs, A + done);
-                ctx->launches++;
-                done += batch;
-            }
-        }
-        k_finish_windows<<<cdiv((size_t)nwg * 4, 128), 128, 0, sr>>>(S_in, A, li, nwg, d_windows + w0);
+    ge_p3_raw *pool = (ge_p3_raw *)ctx->red_a.p, *A = (ge_p3_raw *)ctx->red_b.p;
+    const ge_p3_raw *S_in = buckets;
+    uint32_t n_in = nb;
+    size_t pos = 0;
+    std::vector<std::pair<size_t, uint32_t>> w_arrays;        // (offset of W array, n_out) per level
+    for (int l = 0; l < li.nlevels; l++) {
+        uint32_t m = lvl_m[l], n_out = lvl_nout[l];
+        ge_p3_raw *S_out = pool + pos, *W_out = pool + pos + (size_t)n_out * nwin;
+        k_chunk_reduce<<<cdiv((size_t)n_out * nwin * 4, 128), 128, 0, st>>>(S_in, n_in, m, l == 0 ? 1u : 0u, n_out, nwin, S_out, W_out);
         ctx->launches++;
-        if (d_result) {
-            k_horner_step<<<1, 32, 0, sr>>>(state, d_windows, w1, w0, c, g == 0);
+        w_arrays.push_back({pos + (size_t)n_out * nwin, n_out});
+        S_in = S_out; n_in = n_out; pos += 2 * (size_t)n_out * nwin;
+    }
+    {   // plain sums of every (level, window) W array: one CTA each
+        SumArrays arrs;
+        int total = li.nlevels * nwin, done = 0;
+        while (done < total) {
+            int batch = std::min(160, total - done);
+            for (int k = 0; k < batch; k++) {
+                int id = done + k, l = id / nwin, w = id % nwin;
+                arrs.off[k] = (uint32_t)(w_arrays[l].first + (size_t)w * w_arrays[l].second);
+                arrs.len[k] = w_arrays[l].second;
+            }
+            k_plain_sum<<<batch, 128, 0, st>>>(pool, arrs, A + done);
             ctx->launches++;
+            done += batch;
         }
     }
-    ctx->last_kernel_launches = G;
-    if (G > 1) {
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join2, sb));
-        CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join2, 0));
-    }
+    k_finish_windows<<<cdiv((size_t)nwin * 4, 128), 128, 0, st>>>(S_in, A, li, nwin, d_windows);
+    ctx->launches++;
     if (d_result) {
-        k_encode<<<1, 32, 0, st>>>(state, d_result);
+        k_combine<<<1, 32, 0, st>>>(d_windows, 1, nwin, c, d_result);
         ctx->launches++;
     }
     CUDA_TRY(ctx, cudaGetLastError());
@@ -717,13 +719,17 @@ static int msm_pipeline(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const vo
 int msm_window_sums(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n,
                     int c, ge_p3_raw *d_windows)
 {
-    return msm_pipeline(ctx, d_scalars, d_points, point_kind, n, c, d_windows, nullptr);
+    int rc;
+    if ((rc = msm_accumulate_chunk(ctx, d_scalars, d_points, point_kind, n, c, true))) return rc;
+    return msm_reduce_finish(ctx, c, d_windows, nullptr);
 }
 
 int msm_full(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n, int c,
              ge_p3_raw *d_windows, MsmResult *d_result)
 {
-    return msm_pipeline(ctx, d_scalars, d_points, point_kind, n, c, d_windows, d_result);
+    int rc;
+    if ((rc = msm_accumulate_chunk(ctx, d_scalars, d_points, point_kind, n, c, true))) return rc;
+    return msm_reduce_finish(ctx, c, d_windows, d_result);
 }
 
 int msm_combine_windows(dalek_b200_ctx *ctx, const ge_p3_raw *d_windows, int ranks, int nwin, int c, MsmResult *d_result)

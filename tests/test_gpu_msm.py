@@ -141,3 +141,38 @@ def test_msm_large_algebraic_identity(eng, oracle):
     pb = b"".join(pool_p[j] for j in idx)
     rc, got, _ = eng.edwards_vartime_msm(sb, pb, n)
     assert rc == 0 and got == want
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_msm_host_chunked_streaming(eng, oracle, fmt):
+    """n = 2^18 + 5 host-buffer call: the pairs are streamed in chunks that add onto persistent bucket
+    sums (copy/compute overlap); result must equal the single-shot device path and the identity
+    sum s_i (t_i B) == (sum s_i t_i) B.  Skewed scalars make some buckets heavy in every chunk."""
+    import numpy as np
+    n = (1 << 18) + 5
+    rnd = random.Random(99 + fmt)
+    B = oracle.basepoint()
+    pool_t = [rnd.randrange(pyref.L) for _ in range(32)]
+    pool_pts = [oracle.scalarmul(t.to_bytes(32, "little"), B) for t in pool_t]
+    idx = [rnd.randrange(32) for _ in range(n)]
+    ss = [rnd.randrange(pyref.L) for _ in range(n)]
+    for i in range(0, n, 3):
+        ss[i] = ss[0]                                   # a third of the scalars are equal: heavy buckets
+    k = sum(s * pool_t[j] for s, j in zip(ss, idx)) % pyref.L
+    want = oracle.compress(oracle.scalarmul(k.to_bytes(32, "little"), B))
+    sb = np.frombuffer(b"".join(s.to_bytes(32, "little") for s in ss), dtype=np.uint8).copy()
+    if fmt == 0:
+        enc = [oracle.compress(p) for p in pool_pts]
+        pb = np.frombuffer(b"".join(enc[j] for j in idx), dtype=np.uint8).copy()
+    else:
+        lim = [np.array(oracle.p3_limbs(oracle.add(oracle.double(p), p)), dtype=np.uint64) for p in pool_pts]   # 3P, Z != 1
+        pb = np.stack([lim[j] for j in idx]).copy()
+        k = 3 * k % pyref.L
+        want = oracle.compress(oracle.scalarmul(k.to_bytes(32, "little"), B))
+    for chunks in (4, 1, 3):
+        eng.set_option("host_chunks", chunks)
+        try:
+            rc, got, _ = eng.edwards_vartime_msm(sb, pb, n, point_fmt=fmt)
+        finally:
+            eng.set_option("host_chunks", 2)
+        assert rc == 0 and got == want, chunks

@@ -130,3 +130,43 @@ def test_verify_batch_flat_large(eng, oracle):
     assert eng.verify_batch_flat(flat, offs, sg, pk, n) == OK
     flat[59 * 12345 + 7] ^= 1
     assert eng.verify_batch_flat(flat, offs, sg, pk, n) == VERIFY
+
+
+def test_verify_batch_host_streaming_pieces(eng, oracle):
+    """n = 2^18 + 77 through the host-buffer entry point: the batch is streamed in pieces (copy of piece
+    k+1 overlaps hashing / decompression of piece k).  Signatures come from the GPU signer (byte-exact
+    on TESTVECTORS, see test_gpu_straus_base.py); a sample is re-verified by the oracle."""
+    import hashlib
+    import numpy as np
+    n, nk = (1 << 18) + 77, 128
+    seeds_k = np.stack([np.frombuffer(hashlib.sha512(b"k%d" % k).digest()[:32], dtype=np.uint8) for k in range(nk)])
+    seeds = np.ascontiguousarray(seeds_k[np.arange(n) % nk])
+    lens = (np.arange(n) % 7) * 9 + 3                       # ragged message lengths 3..57
+    offs = np.zeros(n + 1, dtype=np.uint64); offs[1:] = np.cumsum(lens)
+    rng = np.random.Generator(np.random.PCG64(5))
+    flat = rng.integers(0, 256, size=int(offs[-1]), dtype=np.uint8)
+    pks, sigs = eng.sign_batch_flat(seeds, flat, offs, n)
+    pk = np.frombuffer(pks, dtype=np.uint8).copy(); sg = np.frombuffer(sigs, dtype=np.uint8).copy()
+    for i in (0, 1, 70000, n - 1):                          # oracle spot checks of the synthesised inputs
+        m = flat[int(offs[i]):int(offs[i + 1])].tobytes()
+        assert oracle.verify(m, sg[64 * i:64 * i + 64].tobytes(), pk[32 * i:32 * i + 32].tobytes()) == OK
+    for pieces in (4, 1, 3):
+        eng.set_option("verify_pieces", pieces)
+        try:
+            assert eng.verify_batch_flat(flat, offs, sg, pk, n) == OK
+            zs = eng.last_zs(n)
+            sg[64 * (n - 5) + 40] ^= 1                      # corrupt s of a signature in the last piece
+            assert eng.verify_batch_flat(flat, offs, sg, pk, n) == VERIFY
+            sg[64 * (n - 5) + 40] ^= 1
+        finally:
+            eng.set_option("verify_pieces", 4)
+        if pieces == 4:
+            zs4 = zs
+        else:
+            assert zs == zs4                                # the coefficients do not depend on the piece count
+    # z_i of the first transcript chunk agree with the oracle's
+    first = 128
+    msgs = [flat[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(first)]
+    rc, zo = oracle.verify_batch(msgs, [sg[64 * i:64 * i + 64].tobytes() for i in range(first)],
+                                 [pk[32 * i:32 * i + 32].tobytes() for i in range(first)], chunk=128, want_zs=True)
+    assert rc == OK and zs4[:16 * first] == zo
