@@ -52,7 +52,7 @@ void dalek_b200_destroy(dalek_b200_ctx *ctx)
     DevBuf *bufs[] = {&ctx->scalars, &ctx->points_in, &ctx->points, &ctx->digits, &ctx->counts, &ctx->offsets,
                       &ctx->sorted, &ctx->buckets, &ctx->red_a, &ctx->red_b, &ctx->red_c, &ctx->red_d,
                       &ctx->result, &ctx->flags, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->misc3,
-                      &ctx->misc4, &ctx->misc5, &ctx->zs, &ctx->base_table, &ctx->ntasks, &ctx->task_off, &ctx->tasks, &ctx->task_sums, &ctx->msg_offs};
+                      &ctx->misc4, &ctx->misc5, &ctx->zs, &ctx->base_table, &ctx->ntasks, &ctx->task_off, &ctx->tasks, &ctx->task_sums, &ctx->msg_offs, &ctx->sum_desc, &ctx->sum_part, &ctx->key_table};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
@@ -69,6 +69,7 @@ int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value)
     if (!ctx || !name) return DALEK_E_INVALID_ARG;
     if (!strcmp(name, "window_bits")) { if (value != 0 && (value < 4 || value > 20)) return DALEK_E_INVALID_ARG; ctx->opt_window_bits = value; return 0; }
     if (!strcmp(name, "host_chunks")) { if (value < 1 || value > 4) return DALEK_E_INVALID_ARG; ctx->opt_host_chunks = value; return 0; }
+    if (!strcmp(name, "dedupe_keys")) { ctx->opt_dedupe_keys = value ? 1 : 0; return 0; }
     if (!strcmp(name, "verify_pieces")) { if (value < 1 || value > 4) return DALEK_E_INVALID_ARG; ctx->opt_verify_pieces = value; return 0; }
     if (!strcmp(name, "field_f64")) { ctx->opt_field_f64 = value ? 1 : 0; return 0; }
     if (!strcmp(name, "verify_chunk")) { if (value < 1 || value > (1 << 20)) return DALEK_E_INVALID_ARG; ctx->opt_verify_chunk = value; return 0; }

@@ -170,31 +170,25 @@ __global__ void k_sum_final(const uint32_t *__restrict__ partial, uint32_t count
     }
 }
 
-// decompress R_i (first half of each signature) and A_i of `cnt` signatures into their slots of the
-// MSM point array (out_R = &points[1 + i0], out_A = &points[1 + n + i0]); out_B (slot 0) gets the basepoint
+// decompress R_i (first half of each signature) of `cnt` signatures into out_R = &points[1 + i0];
+// thread cnt writes the basepoint into out_B (slot 0) when given
 __global__ void __launch_bounds__(128)
-k_prep_RA(const uint32_t *__restrict__ sigs, const uint32_t *__restrict__ keys, size_t cnt,
-          ge_niels_packed *__restrict__ out_R, ge_niels_packed *__restrict__ out_A, ge_niels_packed *__restrict__ out_B,
-          int *__restrict__ flags)
+k_prep_R(const uint32_t *__restrict__ sigs, size_t cnt, ge_niels_packed *__restrict__ out_R, ge_niels_packed *__restrict__ out_B,
+         int *__restrict__ flags)
 {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j > 2 * cnt || (j == 2 * cnt && !out_B)) return;
+    if (j > cnt || (j == cnt && !out_B)) return;
     fe x, y;
     ge_niels_packed *dst;
-    if (j == 2 * cnt) {
+    if (j == cnt) {
         fe_const_base_x(x); fe_const_base_y(y);
         dst = out_B;
     } else {
         uint32_t s[8];
-        bool isR = j < cnt;
-        const uint32_t *src = isR ? sigs + 16 * j : keys + 8 * (j - cnt);
-        dst = isR ? out_R + j : out_A + (j - cnt);
 #pragma unroll
-        for (int k = 0; k < 8; k++) s[k] = src[k];
-        if (!ge_decompress_affine(x, y, s)) {
-            atomicOr(&flags[isR ? FLAG_BAD_R : FLAG_BAD_A], 1);
-            fe_0(x); fe_1(y);
-        }
+        for (int k = 0; k < 8; k++) s[k] = sigs[16 * j + k];
+        dst = out_R + j;
+        if (!ge_decompress_affine(x, y, s)) { atomicOr(&flags[FLAG_BAD_R], 1); fe_0(x); fe_1(y); }
     }
     ge_niels nl; ge_affine_to_niels(nl, x, y);
     ge_niels_packed p; ge_niels_pack(p, nl);
@@ -203,8 +197,77 @@ k_prep_RA(const uint32_t *__restrict__ sigs, const uint32_t *__restrict__ keys, 
     for (int k = 0; k < 6; k++) o[k] = make_uint4(p.w[4 * k], p.w[4 * k + 1], p.w[4 * k + 2], p.w[4 * k + 3]);
 }
 
+// Public keys repeat in real batches (the reference's VerifyingKey even carries its decompressed
+// point, E/verifying.rs:65-71, so verify_batch never decompresses A at all).  Keys are de-duplicated
+// with an open-addressing table of signature indices: the first signature that inserts a key becomes
+// its representative and is appended to `uniq`; only representatives are decompressed.
+__global__ void __launch_bounds__(256)
+k_key_dedupe(const uint32_t *__restrict__ keys /* all n keys */, size_t i0, size_t cnt, uint32_t *__restrict__ table,
+             uint32_t tmask, uint32_t *__restrict__ rep, uint32_t *__restrict__ uniq, uint32_t *__restrict__ uniq_count)
+{
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cnt) return;
+    const uint32_t i = (uint32_t)(i0 + j);
+    uint32_t k[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) k[q] = keys[8 * (size_t)i + q];
+    uint32_t h = k[0] * 0x9E3779B1u ^ k[1] * 0x85EBCA77u ^ k[2] * 0xC2B2AE3Du ^ k[3] * 0x27D4EB2Fu ^
+                 k[4] * 0x165667B1u ^ k[5] * 0xD3A2646Cu ^ k[6] * 0xFD7046C5u ^ k[7] * 0xB55A4F09u;
+    h ^= h >> 15;
+    uint32_t slot = h & tmask;
+    for (;;) {
+        uint32_t cur = atomicCAS(&table[slot], 0xffffffffu, i);
+        if (cur == 0xffffffffu) {                              // first holder of this key
+            rep[i] = i;
+            uniq[atomicAdd(uniq_count, 1u)] = i;
+            return;
+        }
+        uint32_t diff = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) diff |= keys[8 * (size_t)cur + q] ^ k[q];
+        if (diff == 0) { rep[i] = cur; return; }
+        slot = (slot + 1) & tmask;
+    }
+}
+
+// decompress the keys listed in uniq[0 .. *uniq_count) (or, without a list, keys i0 .. i0+cnt) into
+// points_A[index]
+__global__ void __launch_bounds__(128)
+k_prep_A(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ uniq, const uint32_t *__restrict__ uniq_count,
+         size_t i0, size_t cnt, ge_niels_packed *__restrict__ points_A, int *__restrict__ flags)
+{
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i;
+    if (uniq) { if (j >= *uniq_count) return; i = uniq[j]; } else { if (j >= cnt) return; i = i0 + j; }
+    uint32_t s[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = keys[8 * i + k];
+    fe x, y;
+    if (!ge_decompress_affine(x, y, s)) { atomicOr(&flags[FLAG_BAD_A], 1); fe_0(x); fe_1(y); }
+    ge_niels nl; ge_affine_to_niels(nl, x, y);
+    ge_niels_packed p; ge_niels_pack(p, nl);
+    uint4 *o = reinterpret_cast<uint4 *>(points_A + i);
+#pragma unroll
+    for (int k = 0; k < 6; k++) o[k] = make_uint4(p.w[4 * k], p.w[4 * k + 1], p.w[4 * k + 2], p.w[4 * k + 3]);
+}
+
+// points_A[i] = points_A[rep[i]] for the non-representatives of this piece
+__global__ void k_copy_A(const uint32_t *__restrict__ rep, size_t i0, size_t cnt, ge_niels_packed *__restrict__ points_A)
+{
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cnt) return;
+    size_t i = i0 + j;
+    uint32_t r = rep[i];
+    if (r == i) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(points_A + r);
+    uint4 *dst = reinterpret_cast<uint4 *>(points_A + i);
+#pragma unroll
+    for (int k = 0; k < 6; k++) dst[k] = src[k];
+}
+
 // ------------------------------------------------------------------------------------------
-struct VerifyBufs { uint32_t *hrams, *hs, *zsprod, *zs, *scalars; ge_niels_packed *points; int *flags; };
+struct VerifyBufs { uint32_t *hrams, *hs, *zsprod, *zs, *scalars; ge_niels_packed *points; int *flags;
+                    uint32_t *table, tmask, *rep, *uniq, *uniq_count; };
 
 static int verify_reserve(dalek_b200_ctx *ctx, size_t n, VerifyBufs &b)
 {
@@ -222,13 +285,24 @@ static int verify_reserve(dalek_b200_ctx *ctx, size_t n, VerifyBufs &b)
     b.hrams = (uint32_t *)ctx->misc2.p; b.hs = (uint32_t *)ctx->misc3.p; b.zsprod = (uint32_t *)ctx->misc4.p;
     b.zs = (uint32_t *)ctx->zs.p; b.scalars = (uint32_t *)ctx->scalars.p; b.points = (ge_niels_packed *)ctx->points.p;
     b.flags = (int *)ctx->flags.p;
+    // key de-duplication table: power of two >= 2n slots, plus rep[n], uniq[n] and 4 piece counters
+    size_t tsize = 1024;
+    while (tsize < 2 * n) tsize <<= 1;
+    if ((rc = ws_reserve(ctx, ctx->key_table, (tsize + 2 * std::max<size_t>(1, n) + 8) * 4))) return rc;
+    b.table = (uint32_t *)ctx->key_table.p; b.tmask = (uint32_t)(tsize - 1);
+    b.rep = b.table + tsize; b.uniq = b.rep + std::max<size_t>(1, n); b.uniq_count = b.uniq + std::max<size_t>(1, n);
+    if (ctx->opt_dedupe_keys) {
+        CUDA_TRY(ctx, cudaMemsetAsync(b.table, 0xff, tsize * 4, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(b.uniq_count, 0, 32, ctx->stream));
+    }
     return 0;
 }
 
 // Front end for signatures [i0, i1) (i0 a multiple of verify_chunk): hashing, transcript, coefficients on
 // the main (high-priority) stream; decompression on the second stream.  Both wait for `ready` if given.
 static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t *d_msgs, const uint64_t *d_offs,
-                        const uint32_t *d_sigs, const uint32_t *d_keys, size_t n, size_t i0, size_t i1, cudaEvent_t ready)
+                        const uint32_t *d_sigs, const uint32_t *d_keys, size_t n, size_t i0, size_t i1, cudaEvent_t ready,
+                        int piece = 0)
 {
     cudaStream_t st = ctx->stream, st2 = ctx->stream2;
     const size_t cnt = i1 - i0;
@@ -242,9 +316,21 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
         k_transcript<<<cdiv(nchunks, 64), 64, 0, st>>>(b.hrams + 16 * i0, d_sigs + 16 * i0, cnt, chunk, b.zs + 4 * i0);
         ctx->launches += 2;
     }
-    k_prep_RA<<<cdiv(2 * cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, d_keys + 8 * i0, cnt, b.points + 1 + i0, b.points + 1 + n + i0,
-                                                       i0 == 0 ? b.points : nullptr, b.flags);
+    ge_niels_packed *points_A = b.points + 1 + n;
+    k_prep_R<<<cdiv(cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, cnt, b.points + 1 + i0, i0 == 0 ? b.points : nullptr, b.flags);
     ctx->launches++;
+    if (cnt) {
+        if (ctx->opt_dedupe_keys) {
+            uint32_t *uc = b.uniq_count + piece, *ul = b.uniq + i0;      // this piece's list of representatives
+            k_key_dedupe<<<cdiv(cnt, 256), 256, 0, st2>>>(d_keys, i0, cnt, b.table, b.tmask, b.rep, ul, uc);
+            k_prep_A<<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, ul, uc, i0, cnt, points_A, b.flags);
+            k_copy_A<<<cdiv(cnt, 256), 256, 0, st2>>>(b.rep, i0, cnt, points_A);
+            ctx->launches += 3;
+        } else {
+            k_prep_A<<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, nullptr, nullptr, i0, cnt, points_A, b.flags);
+            ctx->launches++;
+        }
+    }
     if (cnt) {
         k_coeffs<<<cdiv(cnt, 128), 128, 0, st>>>(b.zs + 4 * i0, d_sigs + 16 * i0, b.hs + 8 * i0, cnt, b.scalars + 8 * (1 + i0),
                                                  b.scalars + 8 * (1 + n + i0), b.zsprod + 8 * i0);
@@ -348,7 +434,7 @@ int ed25519_b200_verify_batch_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat
             CUDA_TRY(ctx, cudaMemcpyAsync(d_keys + i0 * 32, pubkeys + i0 * 32, cnt * 32, cudaMemcpyHostToDevice, sc));
         }
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_grp[k], sc));
-        if ((rc = verify_front(ctx, b, d_msgs, d_offs, (const uint32_t *)d_sigs, (const uint32_t *)d_keys, n, i0, i1, ctx->ev_grp[k]))) return rc;
+        if ((rc = verify_front(ctx, b, d_msgs, d_offs, (const uint32_t *)d_sigs, (const uint32_t *)d_keys, n, i0, i1, ctx->ev_grp[k], k))) return rc;
     }
     return verify_tail(ctx, b, n);
 }

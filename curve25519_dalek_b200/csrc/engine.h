@@ -28,6 +28,7 @@ struct dalek_b200_ctx {
     long opt_window_bits = 0;
     long opt_verify_chunk = 128;
     long opt_host_chunks = 2;   // host-buffer MSM calls stream the pairs in this many chunks (copy/compute overlap)
+    long opt_dedupe_keys = 1;   // verify_batch decompresses every distinct public key once
     long opt_verify_pieces = 4; // host-buffer verify_batch calls stream the signatures in this many pieces
     long opt_field_f64 = 1;     // bucket kernel on the FP64 pipe (fe64.cuh) instead of IMAD.WIDE (fe.cuh)
     // timing of the dominant kernel in the last call
@@ -35,7 +36,8 @@ struct dalek_b200_ctx {
     int last_kernel_launches = 0;
     // device workspaces (grown on demand, reused across calls)
     DevBuf scalars, points_in, points, digits, counts, offsets, sorted, buckets, red_a, red_b, red_c,
-        red_d, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums, msg_offs;
+        red_d, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums, msg_offs, sum_desc, sum_part, key_table;
+    int sum_desc_c = -1;
     bool base_table_ready = false;
     // pinned host staging
     void *h_pinned = nullptr;

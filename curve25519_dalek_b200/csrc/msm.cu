@@ -112,7 +112,7 @@ int msm_choose_window_bits(const dalek_b200_ctx *ctx, size_t n)
     int best = 4; double best_cost = 1e300;
     for (int c = 4; c <= 20; c++) {
         double W = (double)((253 + c - 1) / c);
-        double cost = W * ((double)n + 2.6 * (double)(1u << (c - 1)));
+        double cost = W * ((double)n + 4.0 * (double)(1u << (c - 1)));
         if (cost < best_cost) { best_cost = cost; best = c; }
     }
     return best;
@@ -205,12 +205,15 @@ __global__ void __launch_bounds__(1024) k_scan_apply(const uint32_t *__restrict_
     for (int k = 0; k < 4; k++) { if (base + k < nbuckets) dst[base + k] = run; run += v[k]; }
 }
 
+// Launched per group of windows [w0, w1) sized so that the group's slice of `sorted` stays in L2: the
+// 4-byte scattered writes of one 32-byte sector then merge in L2 instead of each costing a DRAM
+// read-modify-write.
 __global__ void k_scatter(const uint64_t *__restrict__ entries, const uint32_t *__restrict__ offsets, size_t n,
-                          int nwin, uint32_t nbuckets, uint32_t *__restrict__ sorted)
+                          int w0, int w1, uint32_t nbuckets, uint32_t *__restrict__ sorted)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    for (int w = 0; w < nwin; w++) {
+    for (int w = w0; w < w1; w++) {
         uint64_t e = entries[(size_t)w * n + i];
         int32_t d = (int32_t)(e >> 32);
         if (d == 0) continue;
@@ -470,14 +473,17 @@ k_chunk_reduce(const ge_p3_raw *__restrict__ S_in, uint32_t n_in, uint32_t m, ui
 
 // plain sum of one array per CTA (blockIdx.x = array id): 32 groups take strided items, then a
 // shared-memory tree over the 32 partial sums
-struct SumArrays { uint32_t off[160]; uint32_t len[160]; };
+// Arrays are described by (offset, length) pairs in device memory (fixed per window width, cached in the
+// context).  Two stages: pieces of at most SUM_PIECE items, then the per-array sum of the piece sums.
+#define SUM_PIECE 256u
 __global__ void __launch_bounds__(128)
-k_plain_sum(const ge_p3_raw *__restrict__ pool, SumArrays arrs, ge_p3_raw *__restrict__ out)
+k_plain_sum(const ge_p3_raw *__restrict__ pool, const uint2 *__restrict__ desc, ge_p3_raw *__restrict__ out)
 {
     __shared__ ge_p3_raw sh[32];
     const uint32_t role = threadIdx.x & 3, grp = threadIdx.x >> 2;
-    const ge_p3_raw *a = pool + arrs.off[blockIdx.x];
-    const uint32_t len = arrs.len[blockIdx.x];
+    const uint2 d = desc[blockIdx.x];
+    const ge_p3_raw *a = pool + d.x;
+    const uint32_t len = d.y;
     w4_point acc, x;
     w4_identity(acc);
     for (uint32_t i0 = 0; i0 < len; i0 += 32) {
@@ -633,8 +639,11 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
     k_task_fill<<<cdiv(total_buckets, 256), 256, 0, st>>>(ntasks, task_off, win_base, nb, (uint32_t)total_buckets, tasks);
     ctx->launches += 9;
     if (n) {
-        k_scatter<<<cdiv(n, 256), 256, 0, st>>>(entries, offsets, n, nwin, nb, sorted);
-        ctx->launches++;
+        const int wg = (int)std::max<size_t>(1, std::min<size_t>((size_t)nwin, ((size_t)64 << 20) / (n * 4)));
+        for (int w0 = 0; w0 < nwin; w0 += wg) {
+            k_scatter<<<cdiv(n, 256), 256, 0, st>>>(entries, offsets, n, w0, std::min(nwin, w0 + wg), nb, sorted);
+            ctx->launches++;
+        }
     }
     if (first) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st));
     {
@@ -691,20 +700,29 @@ int msm_reduce_finish(dalek_b200_ctx *ctx, int c, ge_p3_raw *d_windows, MsmResul
         w_arrays.push_back({pos + (size_t)n_out * nwin, n_out});
         S_in = S_out; n_in = n_out; pos += 2 * (size_t)n_out * nwin;
     }
-    {   // plain sums of every (level, window) W array: one CTA each
-        SumArrays arrs;
-        int total = li.nlevels * nwin, done = 0;
-        while (done < total) {
-            int batch = std::min(160, total - done);
-            for (int k = 0; k < batch; k++) {
-                int id = done + k, l = id / nwin, w = id % nwin;
-                arrs.off[k] = (uint32_t)(w_arrays[l].first + (size_t)w * w_arrays[l].second);
-                arrs.len[k] = w_arrays[l].second;
+    {   // plain sums of every (level, window) W array, two stages; descriptors depend only on c
+        std::vector<uint2> d1, d2;
+        for (int l = 0; l < li.nlevels; l++)
+            for (int w = 0; w < nwin; w++) {
+                uint32_t off = (uint32_t)(w_arrays[l].first + (size_t)w * w_arrays[l].second), len = w_arrays[l].second;
+                uint32_t first_piece = (uint32_t)d1.size();
+                for (uint32_t o = 0; o < len; o += SUM_PIECE) d1.push_back(make_uint2(off + o, std::min(SUM_PIECE, len - o)));
+                d2.push_back(make_uint2(first_piece, (uint32_t)d1.size() - first_piece));
             }
-            k_plain_sum<<<batch, 128, 0, st>>>(pool, arrs, A + done);
-            ctx->launches++;
-            done += batch;
+        const size_t n1 = d1.size(), n2 = d2.size();
+        if ((rc = ws_reserve(ctx, ctx->sum_desc, (n1 + n2) * sizeof(uint2)))) return rc;
+        if ((rc = ws_reserve(ctx, ctx->sum_part, n1 * sizeof(ge_p3_raw)))) return rc;
+        uint2 *dd1 = (uint2 *)ctx->sum_desc.p, *dd2 = dd1 + n1;
+        if (ctx->sum_desc_c != c) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(dd1, d1.data(), n1 * sizeof(uint2), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(ctx, cudaMemcpyAsync(dd2, d2.data(), n2 * sizeof(uint2), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));       // d1/d2 are host temporaries (rare: once per width)
+            ctx->sum_desc_c = c;
         }
+        ge_p3_raw *parts = (ge_p3_raw *)ctx->sum_part.p;
+        k_plain_sum<<<(unsigned)n1, 128, 0, st>>>(pool, dd1, parts);
+        k_plain_sum<<<(unsigned)n2, 128, 0, st>>>(parts, dd2, A);
+        ctx->launches += 2;
     }
     k_finish_windows<<<cdiv((size_t)nwin * 4, 128), 128, 0, st>>>(S_in, A, li, nwin, d_windows);
     ctx->launches++;

@@ -170,3 +170,31 @@ def test_verify_batch_host_streaming_pieces(eng, oracle):
     rc, zo = oracle.verify_batch(msgs, [sg[64 * i:64 * i + 64].tobytes() for i in range(first)],
                                  [pk[32 * i:32 * i + 32].tobytes() for i in range(first)], chunk=128, want_zs=True)
     assert rc == OK and zs4[:16 * first] == zo
+
+
+def test_verify_batch_key_dedupe(eng, oracle):
+    """Repeated public keys are decompressed once (dedupe_keys option): verdicts, coefficients and error
+    codes must not depend on the option, including an undecodable key that appears several times."""
+    rnd = random.Random(77)
+    seeds = [rnd.randbytes(32) for _ in range(5)]
+    msgs = [rnd.randbytes(40) for _ in range(60)]
+    pks = [oracle.public_key(seeds[i % 5]) for i in range(60)]
+    sigs = [oracle.sign(msgs[i], seeds[i % 5]) for i in range(60)]
+    bad_key = (2).to_bytes(32, "little")
+    for opt in (1, 0):
+        eng.set_option("dedupe_keys", opt)
+        try:
+            assert run(eng, msgs, sigs, pks) == OK
+            zs = eng.last_zs(60)
+            b = list(sigs); x = bytearray(b[17]); x[35] ^= 4; b[17] = bytes(x)
+            assert run(eng, msgs, b, pks) == VERIFY == oracle.verify_batch(msgs, b, pks)
+            k = list(pks); k[3] = bad_key; k[44] = bad_key
+            assert run(eng, msgs, sigs, k) == POINTDEC == oracle.verify_batch(msgs, sigs, k)
+            wrong = list(pks); wrong[10] = pks[11]                 # valid key, wrong signer
+            assert run(eng, msgs, sigs, wrong) == VERIFY
+        finally:
+            eng.set_option("dedupe_keys", 1)
+        if opt == 1:
+            z1 = zs
+        else:
+            assert zs == z1
