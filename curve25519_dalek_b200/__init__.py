@@ -8,8 +8,8 @@ touches the CPU checker used by the tests.  Names follow the reference:
   RistrettoPoint.multiscalar_mul / vartime_multiscalar_mul (src/ristretto.rs:964-994)
   verify_batch (ed25519-dalek/src/batch.rs:146-251) and its SignatureError values.
 """
-from .engine import (Engine, EdwardsPoint, RistrettoPoint, SignatureError, verify_batch, default_engine,
+from .engine import (Engine, EngineError, EdwardsPoint, RistrettoPoint, SignatureError, verify_batch, default_engine,
                      library_path, load_library, POINTS_COMPRESSED, POINTS_EXTENDED)
 
-__all__ = ["Engine", "EdwardsPoint", "RistrettoPoint", "SignatureError", "verify_batch", "default_engine",
+__all__ = ["Engine", "EngineError", "EdwardsPoint", "RistrettoPoint", "SignatureError", "verify_batch", "default_engine",
            "library_path", "load_library", "POINTS_COMPRESSED", "POINTS_EXTENDED"]

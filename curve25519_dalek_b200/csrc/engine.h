@@ -28,6 +28,7 @@ struct dalek_b200_ctx {
     long opt_window_bits = 0;
     long opt_verify_chunk = 128;
     long opt_host_chunks = 2;   // host-buffer MSM calls stream the pairs in this many chunks (copy/compute overlap)
+    long opt_double_base_comb = 1; // double-base batch through the shared-memory fixed-base comb (0 = per-pair Straus)
     long opt_dedupe_keys = 1;   // verify_batch decompresses every distinct public key once
     long opt_verify_pieces = 4; // host-buffer verify_batch calls stream the signatures in this many pieces
     long opt_field_f64 = 1;     // bucket kernel on the FP64 pipe (fe64.cuh) instead of IMAD.WIDE (fe.cuh)

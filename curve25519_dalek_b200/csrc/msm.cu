@@ -7,12 +7,15 @@
 //
 //   k_digits            one thread per scalar: signed radix-2^c digits (scalar.rs:1093-1150
 //                       generalised to c > 8), histogram of bucket sizes, rank inside the bucket
-//   k_scan_window       one CTA per window: exclusive scan of the bucket sizes
+//   k_scan_*            exclusive scan of the bucket sizes per window (multi-block)
 //   k_scatter           counting-sort scatter: point indices grouped by (window, bucket)
-//   k_bucket_accumulate one thread per bucket: sum of its points with the complete unified
-//                       mixed addition (curve_models.rs:411-494), 7M (affine Niels) or 8M
-//   k_reduce_level      sum_k k*B_k per window by chunked running sums (pippenger.rs:146-151),
-//                       log-depth across chunks
+//   k_task_*            buckets cut into tasks of <= 64 entries (skewed / adversarial inputs)
+//   k_bucket_accumulate one thread per task: sum of its points with the complete unified mixed
+//                       addition (curve_models.rs:411-494), 7M (affine Niels) or 8M, on the
+//                       FP64-pipe field (fe64.cuh) with cp.async point prefetch
+//   k_heavy_fixup       sums the task sums of buckets that were cut
+//   k_chunk_reduce, k_plain_sum, k_finish_windows
+//                       sum_k k*B_k per window (pippenger.rs:146-151) in log depth on 4-lane groups
 //   k_combine           total = total*2^c + window (pippenger.rs:159), compress
 //
 // Data layout in HBM: scalars n x 32 B; points packed Niels (96 B) or projective Niels (128 B),
@@ -224,24 +227,34 @@ __global__ void k_scatter(const uint64_t *__restrict__ entries, const uint32_t *
 }
 
 // ------------------------------------------------------------------------------------------
-// Bucket accumulation as a list of tasks.  A task is at most TASK_LEN consecutive entries of one
+// Bucket accumulation as a list of tasks.  A task is at most task_len consecutive entries of one
 // bucket; a bucket with more entries (skewed inputs: the 128-bit z_i of verify_batch put n/256
 // points into each of 256 buckets of one window; adversarial inputs can put everything into one)
 // is cut into several tasks whose partial sums are added afterwards by k_heavy_fixup.  Inside a
 // CTA the 128 tasks are sorted by length so that the lanes of a warp run the same trip count.
-#define TASK_LEN 64u
+// task_len (msm_task_len) is twice the mean bucket size when the buckets alone give enough parallelism,
+// so that only genuinely skewed buckets are cut; with few buckets it is what yields >= 2^18 tasks.
+#define TASK_LEN_MIN 64u
+static uint32_t msm_task_len(size_t n, int nwin, uint32_t nb)
+{
+    const size_t total_buckets = (size_t)nwin * nb;
+    const size_t want = total_buckets >= ((size_t)1 << 18) ? 2 * (n / nb) : (n * (size_t)nwin) >> 18;
+    uint32_t len = TASK_LEN_MIN;
+    while (len < want && len < (1u << 22)) len <<= 1;
+    return len;
+}
 #ifndef ACC_MIN_BLOCKS
 #define ACC_MIN_BLOCKS 4
 #endif
 
 // also appends every bucket that needs more than one task to the heavy list (heavy[0] = count)
-__global__ void k_task_count(const uint32_t *__restrict__ counts, uint32_t total_buckets, uint32_t *__restrict__ ntasks,
-                             uint32_t *__restrict__ heavy)
+__global__ void k_task_count(const uint32_t *__restrict__ counts, uint32_t total_buckets, uint32_t task_len,
+                             uint32_t *__restrict__ ntasks, uint32_t *__restrict__ heavy)
 {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_buckets) return;
     uint32_t c = counts[t];
-    uint32_t k = c <= TASK_LEN ? 1u : (c + TASK_LEN - 1) / TASK_LEN;
+    uint32_t k = c <= task_len ? 1u : (c + task_len - 1) / task_len;
     ntasks[t] = k;
     if (k > 1) heavy[1 + atomicAdd(&heavy[0], 1u)] = t;
 }
@@ -286,7 +299,7 @@ __global__ void __launch_bounds__(128, ACC_MIN_BLOCKS)
 k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict__ sorted,
                     const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets,
                     const uint32_t *__restrict__ ntasks, const uint2 *__restrict__ tasks,
-                    const uint32_t *__restrict__ win_base, int w0, int w1, size_t n, uint32_t nbuckets,
+                    const uint32_t *__restrict__ win_base, int w0, int w1, size_t n, uint32_t nbuckets, uint32_t task_len,
                     ge_p3_raw *__restrict__ buckets, ge_p3_raw *__restrict__ task_sums, int first)
 {
     __shared__ uint32_t s_key[128];     // (len << 8) | local task index, sorted descending
@@ -298,8 +311,8 @@ k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict_
         uint32_t p = p0 + threadIdx.x, len = 0;
         if (p < total_tasks) {
             uint2 tk = tasks[p];
-            uint32_t cnt = counts[tk.x], start = tk.y * TASK_LEN;
-            len = min(TASK_LEN, cnt - start) + 1;            // +1: empty tasks still sort above padding
+            uint32_t cnt = counts[tk.x], start = tk.y * task_len;
+            len = min(task_len, cnt - start) + 1;            // +1: empty tasks still sort above padding
         }
         s_key[threadIdx.x] = (len << 8) | threadIdx.x;
         __syncthreads();
@@ -321,8 +334,8 @@ k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict_
     const uint32_t p = p0 + (key & 0xff);
     const uint2 tk = tasks[p];
     const uint32_t t = tk.x, w = t / nbuckets;
-    const uint32_t cnt = counts[t], start = tk.y * TASK_LEN;
-    const uint32_t len = min(TASK_LEN, cnt - start);
+    const uint32_t cnt = counts[t], start = tk.y * task_len;
+    const uint32_t len = min(task_len, cnt - start);
     // `first` = first chunk of points: buckets start at the identity.  Later chunks (host inputs are
     // streamed in chunks so that the copies overlap the arithmetic) add onto the stored bucket sums;
     // the stored sum is folded in by piece 0 of the bucket (or by k_heavy_fixup for split buckets).
@@ -556,37 +569,6 @@ k_combine(const ge_p3_raw *__restrict__ windows, int ranks, int nwin, int c, Msm
     res->pad = 0;
 }
 
-// Horner continued over one window group: state = state * 2^(c * count) + ... (windows w_hi-1 .. w_lo).
-// `first` = the group holding the top window (state starts at the identity, no leading doublings).
-__global__ void __launch_bounds__(32)
-k_horner_step(ge_p3_raw *__restrict__ state, const ge_p3_raw *__restrict__ windows, int w_hi, int w_lo, int c, int first)
-{
-    const uint32_t role = threadIdx.x & 3;
-    w4_point tot, x;
-    if (first) w4_identity(tot); else w4_load(tot, state);
-    for (int w = w_hi - 1; w >= w_lo; w--) {
-        if (!(first && w == w_hi - 1))
-            for (int k = 0; k < c; k++) w4_dbl(tot, role, k == c - 1);
-        w4_load(x, windows + w);
-        w4_add(tot, x, role);
-    }
-    if (threadIdx.x < 4) w4_store(state, tot, role);
-}
-
-__global__ void k_encode(const ge_p3_raw *__restrict__ state, MsmResult *__restrict__ res)
-{
-    if (threadIdx.x || blockIdx.x) return;
-    ge_p3 total; load_p3(total, state);
-    uint32_t s[8];
-    ge_compress(s, total);
-#pragma unroll
-    for (int i = 0; i < 8; i++) res->compressed[i] = s[i];
-    fe_to_limbs51(res->limbs, total.X); fe_to_limbs51(res->limbs + 5, total.Y);
-    fe_to_limbs51(res->limbs + 10, total.Z); fe_to_limbs51(res->limbs + 15, total.T);
-    res->is_identity = ge_is_identity(total);
-    res->pad = 0;
-}
-
 // ------------------------------------------------------------------------------------------
 // One chunk of (scalar, point) pairs: digits, counting sort, task lists and bucket accumulation.
 // `first` chunks start the buckets at the identity; later chunks add onto them.  All chunks of one
@@ -597,8 +579,9 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
     const int nwin = msm_window_count_for_bits(c);
     const uint32_t nb = 1u << (c - 1);
     const size_t total_buckets = (size_t)nwin * nb;
-    const size_t max_tasks = total_buckets + (std::max<size_t>(1, n) * nwin) / TASK_LEN + 1;
-    const size_t max_heavy = (std::max<size_t>(1, n) * nwin) / TASK_LEN + 1;
+    const uint32_t task_len = msm_task_len(n, nwin, nb);
+    const size_t max_tasks = total_buckets + (std::max<size_t>(1, n) * nwin) / task_len + 1;
+    const size_t max_heavy = (std::max<size_t>(1, n) * nwin) / task_len + 1;
     const uint32_t parts = (nb + SCAN_PART - 1) / SCAN_PART;
     cudaStream_t st = ctx->stream;
     int rc;
@@ -631,7 +614,7 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
     k_scan_partial<<<nwin * parts, 1024, 0, st>>>(counts, nb, parts, part_sums);
     k_scan_bases<<<nwin, 32, 0, st>>>(part_sums, parts);
     k_scan_apply<<<nwin * parts, 1024, 0, st>>>(counts, part_sums, nb, parts, offsets);
-    k_task_count<<<cdiv(total_buckets, 256), 256, 0, st>>>(counts, (uint32_t)total_buckets, ntasks, heavy);
+    k_task_count<<<cdiv(total_buckets, 256), 256, 0, st>>>(counts, (uint32_t)total_buckets, task_len, ntasks, heavy);
     k_scan_partial<<<nwin * parts, 1024, 0, st>>>(ntasks, nb, parts, part_sums);
     k_scan_bases<<<nwin, 32, 0, st>>>(part_sums, parts);
     k_scan_apply<<<nwin * parts, 1024, 0, st>>>(ntasks, part_sums, nb, parts, task_off);
@@ -649,7 +632,7 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
     {
         const unsigned grid = cdiv(max_tasks, 128);
         const int f = first ? 1 : 0;
-#define LAUNCH_ACC(KIND_, F64_) k_bucket_accumulate<KIND_, F64_><<<grid, 128, 0, st>>>(d_points, sorted, counts, offsets, ntasks, tasks, win_base, 0, nwin, n, nb, buckets, task_sums, f)
+#define LAUNCH_ACC(KIND_, F64_) k_bucket_accumulate<KIND_, F64_><<<grid, 128, 0, st>>>(d_points, sorted, counts, offsets, ntasks, tasks, win_base, 0, nwin, n, nb, task_len, buckets, task_sums, f)
         if (point_kind == PK_NIELS) { if (ctx->opt_field_f64) LAUNCH_ACC(PK_NIELS, 1); else LAUNCH_ACC(PK_NIELS, 0); }
         else { if (ctx->opt_field_f64) LAUNCH_ACC(PK_PNIELS, 1); else LAUNCH_ACC(PK_PNIELS, 0); }
 #undef LAUNCH_ACC

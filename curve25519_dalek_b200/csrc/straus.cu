@@ -15,6 +15,7 @@
 
 #include "../../include/dalek_b200.h"
 #include "engine.h"
+#include "ge64.cuh"
 
 static inline unsigned cdiv(size_t a, unsigned b) { return (unsigned)((a + b - 1) / b); }
 void launch_niels_to_pniels(dalek_b200_ctx *ctx, const void *in, void *out, size_t n);
@@ -215,35 +216,171 @@ k_double_base(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, co
     for (int k = 0; k < 8; k++) out[8 * i + k] = enc[k];
 }
 
+// ---- fixed-base comb for the double-base batch ------------------------------------------------
+// With G and H shared by the whole batch, a*G + b*H = sum_i a_i (16^i G) + b_i (16^i H) over the radix-16
+// signed digits (scalar.rs:1019-1051): 128 mixed additions per pair and NO doublings, against 256
+// doublings + 128 additions for Straus.  The contract of MultiscalarMul is kept: the 2 x 64 x 8 table
+// entries (j+1) 16^i {G,H} sit in shared memory as balanced FP64 limbs (15 doubles each, 120 KiB), every
+// lookup scans all 8 entries of a row at warp-uniform addresses with arithmetic masks (window.rs:54-76),
+// and the digit's sign is applied by masked swap / negate inside the addition.
+#define COMB_ROWS 128          // 2 bases x 64 digit positions
+#define COMB_ENTRY 15          // doubles per affine Niels entry
+
+__global__ void __launch_bounds__(128)
+k_comb_tables(const uint32_t *__restrict__ GH, double *__restrict__ table, int *__restrict__ status)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= COMB_ROWS * 8) return;
+    int b = t >> 9, i = (t >> 3) & 63, j = t & 7;
+    uint32_t enc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) enc[k] = GH[8 * b + k];
+    ge_p3 base, P;
+    if (!ristretto_decompress(base, enc)) { atomicOr(status, 1); ge_p3_identity(base); }
+    ge_pniels nb; ge_p3_to_pniels(nb, base);
+    P = base;
+    for (int k = 0; k < j; k++) ge_padd(P, P, nb, 0);            // (j+1) * base
+    if (i) ge_mul_by_pow_2(P, P, 4 * i);                         // * 16^i
+    fe zi, x, y;
+    fe_invert(zi, P.Z);
+    fe_mul(x, P.X, zi); fe_mul(y, P.Y, zi);
+    ge_niels n; ge_affine_to_niels(n, x, y);
+    fe64 e[3];
+    fe64_from_fe(e[0], n.ypx); fe64_from_fe(e[1], n.ymx); fe64_from_fe(e[2], n.xy2d);
+    double *dst = table + (size_t)t * COMB_ENTRY;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int k = 0; k < 5; k++) dst[5 * c + k] = e[c].v[k];
+}
+
+// constant-time: select |digit| * 16^i * base from the 8 entries of one table row (digit 0 -> identity)
+__device__ __forceinline__ void comb_select(ge64_niels &q, const double *__restrict__ row, uint32_t xabs)
+{
+    long long w[COMB_ENTRY];
+#pragma unroll
+    for (int k = 0; k < COMB_ENTRY; k++) w[k] = 0;
+#pragma unroll 1
+    for (uint32_t j = 1; j <= 8; j++) {
+        const long long m = 0LL - (long long)(xabs == j);
+#pragma unroll
+        for (int k = 0; k < COMB_ENTRY; k++) w[k] |= __double_as_longlong(row[(j - 1) * COMB_ENTRY + k]) & m;
+    }
+    const long long one = 0x3ff0000000000000LL & (0LL - (long long)(xabs == 0));      // 1.0 for the identity (1, 1, 0)
+    w[0] |= one; w[5] |= one;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        q.ypx.v[k] = __longlong_as_double(w[k]); q.ymx.v[k] = __longlong_as_double(w[5 + k]); q.xy2d.v[k] = __longlong_as_double(w[10 + k]);
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+k_double_base_comb(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, const double *__restrict__ table, size_t n,
+                   uint32_t *__restrict__ out)
+{
+    extern __shared__ double s_tab[];                             // COMB_ROWS * 8 * COMB_ENTRY doubles
+    for (int k = threadIdx.x; k < COMB_ROWS * 8 * COMB_ENTRY; k += blockDim.x) s_tab[k] = table[k];
+    __syncthreads();
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge64_p3 acc; ge64_identity(acc);
+    int ca = 0, cb = 0;                                           // radix-16 recoding carries (scalar.rs:1040-1046)
+    uint32_t wa = 0, wb = 0;
+#pragma unroll 1
+    for (int pos = 0; pos < 64; pos++) {
+        if ((pos & 7) == 0) { wa = a[8 * i + (pos >> 3)]; wb = b[8 * i + (pos >> 3)]; }   // one scalar word per 8 digits
+        int da = (int)(wa & 15) + ca; wa >>= 4;
+        int db = (int)(wb & 15) + cb; wb >>= 4;
+        if (pos < 63) { ca = (da + 8) >> 4; da -= ca << 4; cb = (db + 8) >> 4; db -= cb << 4; }
+        ge64_niels q;
+        int m = da >> 31;
+        comb_select(q, s_tab + (size_t)pos * 8 * COMB_ENTRY, (uint32_t)((da + m) ^ m));
+        ge64_madd(acc, acc, q, (uint32_t)(da < 0));
+        m = db >> 31;
+        comb_select(q, s_tab + (size_t)(64 + pos) * 8 * COMB_ENTRY, (uint32_t)((db + m) ^ m));
+        ge64_madd(acc, acc, q, (uint32_t)(db < 0));
+    }
+    ge_p3 Q; ge64_to_p3(Q, acc);
+    uint32_t enc[8];
+    ristretto_compress(enc, Q);
+#pragma unroll
+    for (int k = 0; k < 8; k++) out[8 * i + k] = enc[k];
+}
+
+// Table build for one (G, H) pair on ctx->stream; returns the device table and which kernel reads it.
+struct DoubleBasePlan { const void *table; int *d_status; int variant; size_t smem; };
+
+static int double_base_setup(dalek_b200_ctx *ctx, const uint8_t G[32], const uint8_t H[32], size_t n, DoubleBasePlan &plan)
+{
+    int rc;
+    cudaStream_t st = ctx->stream;
+    const size_t comb_bytes = (size_t)COMB_ROWS * 8 * COMB_ENTRY * sizeof(double);
+    const size_t head = 64 + 2 * 8 * 40 * 4 + 64;
+    if ((rc = ws_reserve(ctx, ctx->misc0, head + comb_bytes))) return rc;
+    uint32_t *d_gh = (uint32_t *)ctx->misc0.p;
+    uint32_t *d_tables = d_gh + 16;
+    plan.d_status = (int *)(d_tables + 640);
+    double *d_comb = (double *)((char *)ctx->misc0.p + head);
+    if ((rc = pinned_reserve(ctx, 256))) return rc;
+    memcpy(ctx->h_pinned, G, 32); memcpy((char *)ctx->h_pinned + 32, H, 32);
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_gh, ctx->h_pinned, 64, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(plan.d_status, 0, 4, st));
+    const bool comb = ctx->opt_double_base_comb && n >= 4096;     // the table build only pays off for a real batch
+    if (comb) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(k_double_base_comb<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)comb_bytes));
+            attr_set = true;
+        }
+        k_comb_tables<<<8, 128, 0, st>>>(d_gh, d_comb, plan.d_status);
+        plan.table = d_comb; plan.variant = 1; plan.smem = comb_bytes;
+    } else {
+        k_double_base_tables<<<1, 32, 0, st>>>(d_gh, d_tables, plan.d_status);
+        plan.table = d_tables; plan.variant = 0; plan.smem = 0;
+    }
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+static int double_base_launch(dalek_b200_ctx *ctx, const DoubleBasePlan &plan, const uint8_t *d_a, const uint8_t *d_b, size_t n,
+                              uint8_t *d_out, cudaStream_t st)
+{
+    if (!n) return 0;
+    const uint32_t *a = (const uint32_t *)d_a, *b = (const uint32_t *)d_b;
+    // 384 threads x 168 registers fill the register file with the 120 KiB table resident (512 x 128 spills; measured slower)
+    if (plan.variant == 1) k_double_base_comb<384><<<cdiv(n, 384), 384, plan.smem, st>>>(a, b, (const double *)plan.table, n, (uint32_t *)d_out);
+    else k_double_base<<<cdiv(n, 128), 128, 0, st>>>(a, b, (const uint32_t *)plan.table, n, (uint32_t *)d_out);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+static int double_base_status(dalek_b200_ctx *ctx, const DoubleBasePlan &plan, int *h_status)
+{
+    cudaStream_t st = ctx->stream;
+    int *hs = (int *)((char *)ctx->h_pinned + 128);
+    CUDA_TRY(ctx, cudaMemcpyAsync(hs, plan.d_status, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
+    ctx->last_kernel_launches = 1;
+    *h_status = *hs;
+    return 0;
+}
+
+// device-resident scalars in, device-resident encodings out
 int ristretto_double_base(dalek_b200_ctx *ctx, const uint8_t *d_a, const uint8_t *d_b, const uint8_t G[32], const uint8_t H[32],
                           size_t n, uint8_t *d_out, int *h_status)
 {
     int rc;
-    cudaStream_t st = ctx->stream;
-    if ((rc = ws_reserve(ctx, ctx->misc0, 64 + 2 * 8 * 40 * 4 + 64))) return rc;
-    uint32_t *d_gh = (uint32_t *)ctx->misc0.p;
-    uint32_t *d_tables = d_gh + 16;
-    int *d_status = (int *)(d_tables + 640);
-    if ((rc = pinned_reserve(ctx, 256))) return rc;
-    memcpy(ctx->h_pinned, G, 32); memcpy((char *)ctx->h_pinned + 32, H, 32);
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_gh, ctx->h_pinned, 64, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(d_status, 0, 4, st));
-    k_double_base_tables<<<1, 32, 0, st>>>(d_gh, d_tables, d_status);
-    ctx->launches++;
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st));
-    if (n) {
-        k_double_base<<<cdiv(n, 128), 128, 0, st>>>((const uint32_t *)d_a, (const uint32_t *)d_b, d_tables, n, (uint32_t *)d_out);
-        ctx->launches++;
-    }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, st));
-    ctx->last_kernel_launches = 1;
-    int *hs = (int *)((char *)ctx->h_pinned + 128);
-    CUDA_TRY(ctx, cudaMemcpyAsync(hs, d_status, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
-    *h_status = *hs;
-    return 0;
+    DoubleBasePlan plan;
+    if ((rc = double_base_setup(ctx, G, H, n, plan))) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    if ((rc = double_base_launch(ctx, plan, d_a, d_b, n, d_out, ctx->stream))) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+    return double_base_status(ctx, plan, h_status);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -325,24 +462,40 @@ int dalek_b200_ristretto_double_base_batch(dalek_b200_ctx *ctx, const uint8_t *a
 {
     if (!ctx || !G || !H || (n && (!a || !b || !out))) return DALEK_E_INVALID_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    for (size_t i = 0; i < n; i++)
-        if ((a[32 * i + 31] | b[32 * i + 31]) & 0x80) { ctx->last_error = "scalar with bit 255 set (Scalar invariant #1)"; return DALEK_E_INVALID_ARG; }
+    {   // Scalar invariant #1 (scalar.rs:214-230): bit 255 clear
+        uint8_t top = 0;
+        for (size_t i = 0; i < n; i++) top |= a[32 * i + 31] | b[32 * i + 31];
+        if (top & 0x80) { ctx->last_error = "scalar with bit 255 set (Scalar invariant #1)"; return DALEK_E_INVALID_ARG; }
+    }
     int rc;
-    cudaStream_t st = ctx->stream;
     if ((rc = ws_reserve(ctx, ctx->scalars, std::max<size_t>(1, n) * 64))) return rc;
     if ((rc = ws_reserve(ctx, ctx->points_in, std::max<size_t>(1, n) * 32))) return rc;
     uint8_t *d_a = (uint8_t *)ctx->scalars.p, *d_b = d_a + n * 32, *d_out = (uint8_t *)ctx->points_in.p;
-    if (n) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_a, a, n * 32, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_b, b, n * 32, cudaMemcpyHostToDevice, st));
+    DoubleBasePlan plan;
+    if ((rc = double_base_setup(ctx, G, H, n, plan))) return rc;
+    // The batch is independent per pair: pieces alternate between two streams, each doing copy-in -> kernel ->
+    // copy-out, so that the PCIe traffic of one piece (both directions) hides under the arithmetic of its
+    // neighbours.  (With pageable caller memory the copies are staged by the driver and overlap less.)
+    cudaStream_t ss[2] = {ctx->stream, ctx->stream2};
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    const size_t pieces = n >= (1u << 16) ? 8 : 1;
+    for (size_t k = 0; k < pieces; k++) {
+        const size_t lo = n * k / pieces, hi = n * (k + 1) / pieces, m = hi - lo;
+        if (!m) continue;
+        cudaStream_t st = ss[k & 1];
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_a + 32 * lo, a + 32 * lo, 32 * m, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_b + 32 * lo, b + 32 * lo, 32 * m, cudaMemcpyHostToDevice, st));
+        if ((rc = double_base_launch(ctx, plan, d_a + 32 * lo, d_b + 32 * lo, m, d_out + 32 * lo, st))) return rc;
+        CUDA_TRY(ctx, cudaMemcpyAsync(out + 32 * lo, d_out + 32 * lo, 32 * m, cudaMemcpyDeviceToHost, st));
     }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));          // ev_a .. ev_b: device span of the whole batch, copies included
     int status = 0;
-    if ((rc = ristretto_double_base(ctx, d_a, d_b, G, H, n, d_out, &status))) return rc;
-    if (status) return DALEK_NONE;
-    if (n) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, n * 32, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    }
+    if ((rc = double_base_status(ctx, plan, &status))) return rc;
+    if (status) return DALEK_NONE;                                   // G or H does not decode; `out` is unspecified
     return DALEK_OK;
 }
 

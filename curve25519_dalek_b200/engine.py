@@ -164,11 +164,16 @@ class Engine:
         return bytes(out), (list(limbs) if want_limbs else None)
 
     # ---- Ristretto ----
-    def ristretto_double_base_batch(self, a, b, G, H, n):
-        out = (C.c_uint8 * (32 * max(n, 1)))()
+    def ristretto_double_base_batch(self, a, b, G, H, n, out=None):
+        """a_i*G + b_i*H for n pairs (host buffers).  With `out` (a writable 32*n-byte host buffer, e.g. a pinned
+        tensor) the encodings are written there and `out` is returned instead of a bytes copy."""
+        if out is not None:
+            rc = self._check(self.lib.dalek_b200_ristretto_double_base_batch(self.h, _ptr(a), _ptr(b), _ptr(G), _ptr(H), n, _ptr(out)))
+            return rc, out
+        buf = (C.c_uint8 * (32 * max(n, 1)))()
         rc = self._check(self.lib.dalek_b200_ristretto_double_base_batch(self.h, _ptr(a), _ptr(b), _ptr(G), _ptr(H), n,
-                                                                         C.addressof(out)))
-        return rc, bytes(out)[:32 * n]
+                                                                         C.addressof(buf)))
+        return rc, bytes(buf)[:32 * n]
 
     def ristretto_vartime_msm(self, scalars, points, n):
         out = (C.c_uint8 * 32)()

@@ -57,7 +57,11 @@ typedef struct dalek_b200_ctx dalek_b200_ctx;
 int dalek_b200_init(int device, dalek_b200_ctx **out);
 void dalek_b200_destroy(dalek_b200_ctx *ctx);
 const char *dalek_b200_last_error(const dalek_b200_ctx *ctx);
-/* Tunables: "window_bits" (0 = choose from n), "verify_chunk" (transcript chunk, default 128),
+/* Tunables (none changes a result): "window_bits" (4..20, 0 = choose from n), "verify_chunk"
+ * (signatures per transcript, default 128; see verify_batch below), "field_f64" (1 = bucket kernel
+ * on the FP64-pipe field, default; 0 = IMAD.WIDE field), "host_chunks" (1..4, host-buffer MSM calls
+ * stream their input in this many chunks, default 2), "verify_pieces" (1..4, same for verify_batch,
+ * default 4), "dedupe_keys" (1 = decompress every distinct public key once, default).
  * Returns 0 or DALEK_E_INVALID_ARG. */
 int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
@@ -134,8 +138,9 @@ int dalek_b200_ristretto_vartime_msm(dalek_b200_ctx *ctx, const uint8_t *scalars
  *   sigs              n x 64 B R || s                          (signatures: &[Signature])
  *   pubkeys           n x 32 B compressed keys                 (verifying_keys: &[VerifyingKey])
  * In Rust a VerifyingKey already holds its decompressed point (E/verifying.rs:65-71); here keys
- * arrive as bytes and VerifyingKey::from_bytes (E/verifying.rs:167-175) runs inside the call: an
- * undecodable key is ED25519_ERR_POINT_DECOMPRESSION.  Then, in the reference's order
+ * arrive as bytes and VerifyingKey::from_bytes (E/verifying.rs:167-175) runs inside the call (once
+ * per DISTINCT key: repeated keys are de-duplicated on the device): an undecodable key is
+ * ED25519_ERR_POINT_DECOMPRESSION.  Then, in the reference's order
  * (E/batch.rs:208-250): non-canonical s -> ED25519_ERR_SCALAR_FORMAT; undecodable R or a
  * non-identity result -> ED25519_ERR_VERIFY; else 0.  No cofactor multiplication.
  * Coefficients z_i: for n <= verify_chunk the Merlin transcript is exactly the reference's; for

@@ -84,6 +84,68 @@ def test_ristretto_double_base_batch(eng, oracle, kat):
     assert [got[32 * i:32 * i + 32] for i in range(16)] == encs
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_ristretto_double_base_comb(eng, oracle, kat, variant):
+    """Batches of >= 4096 pairs go through the shared-memory fixed-base comb; every variant must give
+    the oracle's bytes (Straus restatement of straus.rs:106-146), edge scalars included."""
+    rnd = random.Random(57)
+    G = bytes.fromhex(kat["constants"]["RISTRETTO_BASEPOINT_COMPRESSED"]["hex"])
+    Gp = oracle.ristretto_decompress(G)
+    Hc = oracle.ristretto_compress(oracle.scalarmul(b32(pyref.labelled_scalar(b"dalek-b200/H", 1, 0)), Gp))
+    n = 4200
+    a = [rnd.randrange(pyref.L) for _ in range(n)]
+    b = [rnd.randrange(pyref.L) for _ in range(n)]
+    edge = [0, 1, 8, 9, 15, 16, pyref.L - 1, pyref.L, 2**255 - 1, 2**252, 0x8888888888888888888888888888888888888888888888888888888888888888 >> 1,
+            0x7777777777777777777777777777777777777777777777777777777777777777]
+    for k, e in enumerate(edge):
+        a[k], b[k] = e, edge[-1 - k]
+        a[100 + k], b[100 + k] = e, 0
+        a[200 + k], b[200 + k] = 0, e
+    a[4199], b[4199] = pyref.L - 1, pyref.L - 1              # last lane of a partial block
+    ab, bb = b"".join(b32(x) for x in a), b"".join(b32(x) for x in b)
+    rc_o, want = oracle.ristretto_double_base_batch(ab, bb, G, Hc)
+    eng.set_option("double_base_comb", variant)
+    try:
+        rc, got = eng.ristretto_double_base_batch(ab, bb, G, Hc, n)
+        assert rc == rc_o == 0
+        bad = [i for i in range(n) if got[32 * i:32 * i + 32] != want[32 * i:32 * i + 32]]
+        assert not bad, bad[:10]
+        rc, _ = eng.ristretto_double_base_batch(ab, bb, b32(1), Hc, n)   # undecodable base -> None
+        assert rc == 1
+    finally:
+        eng.set_option("double_base_comb", 1)
+
+
+def test_ristretto_double_base_streamed_pieces(eng, oracle, kat):
+    """>= 2^16 pairs are streamed in 8 pieces over two streams: both kernels must agree everywhere and match
+    the oracle around every piece boundary and on a random sample."""
+    import numpy as np
+    G = bytes.fromhex(kat["constants"]["RISTRETTO_BASEPOINT_COMPRESSED"]["hex"])
+    Gp = oracle.ristretto_decompress(G)
+    Hc = oracle.ristretto_compress(oracle.scalarmul(b32(pyref.labelled_scalar(b"dalek-b200/H", 1, 0)), Gp))
+    n = 70001
+    rng = np.random.Generator(np.random.PCG64(58))
+    a = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); a[:, 31] &= 0x7F
+    b = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); b[:, 31] &= 0x0F
+    outs = []
+    for variant in (0, 1):
+        eng.set_option("double_base_comb", variant)
+        out = np.zeros(32 * n, dtype=np.uint8)
+        rc, _ = eng.ristretto_double_base_batch(a, b, G, Hc, n, out=out)
+        assert rc == 0
+        outs.append(out.reshape(n, 32))
+    eng.set_option("double_base_comb", 1)
+    assert np.array_equal(outs[0], outs[1])
+    idx = sorted({min(n - 1, max(0, n * k // 8 + d)) for k in range(9) for d in (-1, 0, 1)} | set(rng.integers(0, n, size=150).tolist()))
+    rc, want = oracle.ristretto_double_base_batch(a[idx].tobytes(), b[idx].tobytes(), G, Hc)
+    assert rc == 0 and outs[1][idx].tobytes() == want
+    # a scalar with bit 255 set violates the Scalar invariant: rejected before any work
+    a[n // 2, 31] |= 0x80
+    import curve25519_dalek_b200 as pkg
+    with pytest.raises(pkg.EngineError):
+        eng.ristretto_double_base_batch(a, b, G, Hc, n, out=np.zeros(32 * n, dtype=np.uint8))
+
+
 def test_ristretto_vartime_msm(eng, oracle, kat):
     rnd = random.Random(56)
     G = oracle.ristretto_decompress(bytes.fromhex(kat["constants"]["RISTRETTO_BASEPOINT_COMPRESSED"]["hex"]))
