@@ -95,11 +95,11 @@ k_transcript(const uint32_t *__restrict__ hrams, const uint32_t *__restrict__ si
     }
 }
 
-// out_z[i] = z_i, out_zh[i] = z_i h_i (slots 1+i and 1+n+i of the MSM scalar array; slot 0 is written by
-// k_sum_final); zs_prod[i] = z_i s_i
+// out_z[i] = z_i (MSM scalar of R_i), out_zh[i] = z_i h_i (MSM scalar of A_i, or -- with key merging -- the
+// summand of its key; may alias hs), zs_prod[i] = z_i s_i
 __global__ void __launch_bounds__(128)
-k_coeffs(const uint32_t *__restrict__ zs, const uint32_t *__restrict__ sigs, const uint32_t *__restrict__ hs, size_t n,
-         uint32_t *__restrict__ out_z, uint32_t *__restrict__ out_zh, uint32_t *__restrict__ zs_prod)
+k_coeffs(const uint32_t *__restrict__ zs, const uint32_t *__restrict__ sigs, const uint32_t *hs, size_t n,
+         uint32_t *__restrict__ out_z, uint32_t *out_zh, uint32_t *__restrict__ zs_prod)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -200,10 +200,13 @@ k_prep_R(const uint32_t *__restrict__ sigs, size_t cnt, ge_niels_packed *__restr
 // Public keys repeat in real batches (the reference's VerifyingKey even carries its decompressed
 // point, E/verifying.rs:65-71, so verify_batch never decompresses A at all).  Keys are de-duplicated
 // with an open-addressing table of signature indices: the first signature that inserts a key becomes
-// its representative and is appended to `uniq`; only representatives are decompressed.
+// its representative and is appended to `uniq` (position = the key's dense id); only representatives are
+// decompressed, and the MSM gets ONE term per distinct key whose scalar is the sum of the z_i h_i of its
+// signatures -- the same group equation as batch.rs:240-244 with equal points collected.
 __global__ void __launch_bounds__(256)
 k_key_dedupe(const uint32_t *__restrict__ keys /* all n keys */, size_t i0, size_t cnt, uint32_t *__restrict__ table,
-             uint32_t tmask, uint32_t *__restrict__ rep, uint32_t *__restrict__ uniq, uint32_t *__restrict__ uniq_count)
+             uint32_t tmask, uint32_t *__restrict__ rep, uint32_t *__restrict__ uniq, uint32_t *__restrict__ dense,
+             uint32_t *__restrict__ uniq_count)
 {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= cnt) return;
@@ -219,7 +222,8 @@ k_key_dedupe(const uint32_t *__restrict__ keys /* all n keys */, size_t i0, size
         uint32_t cur = atomicCAS(&table[slot], 0xffffffffu, i);
         if (cur == 0xffffffffu) {                              // first holder of this key
             rep[i] = i;
-            uniq[atomicAdd(uniq_count, 1u)] = i;
+            uint32_t pos = atomicAdd(uniq_count, 1u);
+            uniq[pos] = i; dense[i] = pos;
             return;
         }
         uint32_t diff = 0;
@@ -230,15 +234,15 @@ k_key_dedupe(const uint32_t *__restrict__ keys /* all n keys */, size_t i0, size
     }
 }
 
-// decompress the keys listed in uniq[0 .. *uniq_count) (or, without a list, keys i0 .. i0+cnt) into
-// points_A[index]
+// decompress the keys listed in uniq[*lo .. *hi) into points_A[position] (or, without a list, keys
+// i0 .. i0+cnt into points_A[index])
 __global__ void __launch_bounds__(128)
-k_prep_A(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ uniq, const uint32_t *__restrict__ uniq_count,
-         size_t i0, size_t cnt, ge_niels_packed *__restrict__ points_A, int *__restrict__ flags)
+k_prep_A(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ uniq, const uint32_t *__restrict__ lo,
+         const uint32_t *__restrict__ hi, size_t i0, size_t cnt, ge_niels_packed *__restrict__ points_A, int *__restrict__ flags)
 {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t i;
-    if (uniq) { if (j >= *uniq_count) return; i = uniq[j]; } else { if (j >= cnt) return; i = i0 + j; }
+    size_t i, slot;
+    if (uniq) { slot = *lo + j; if (slot >= *hi) return; i = uniq[slot]; } else { if (j >= cnt) return; i = slot = i0 + j; }
     uint32_t s[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) s[k] = keys[8 * i + k];
@@ -246,28 +250,61 @@ k_prep_A(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ uniq, c
     if (!ge_decompress_affine(x, y, s)) { atomicOr(&flags[FLAG_BAD_A], 1); fe_0(x); fe_1(y); }
     ge_niels nl; ge_affine_to_niels(nl, x, y);
     ge_niels_packed p; ge_niels_pack(p, nl);
-    uint4 *o = reinterpret_cast<uint4 *>(points_A + i);
+    uint4 *o = reinterpret_cast<uint4 *>(points_A + slot);
 #pragma unroll
     for (int k = 0; k < 6; k++) o[k] = make_uint4(p.w[4 * k], p.w[4 * k + 1], p.w[4 * k + 2], p.w[4 * k + 3]);
 }
 
-// points_A[i] = points_A[rep[i]] for the non-representatives of this piece
-__global__ void k_copy_A(const uint32_t *__restrict__ rep, size_t i0, size_t cnt, ge_niels_packed *__restrict__ points_A)
+// all keys distinct: scalar of key `pos` is the z h of its only signature
+__global__ void k_key_gather(const uint32_t *__restrict__ zh, const uint32_t *__restrict__ uniq, size_t nkeys, uint32_t *__restrict__ out)
 {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= cnt) return;
-    size_t i = i0 + j;
-    uint32_t r = rep[i];
-    if (r == i) return;
-    const uint4 *src = reinterpret_cast<const uint4 *>(points_A + r);
-    uint4 *dst = reinterpret_cast<uint4 *>(points_A + i);
+    if (j >= nkeys) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(zh + 8 * (size_t)uniq[j]);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + 8 * j);
+    dst[0] = src[0]; dst[1] = src[1];
+}
+
+// acc[dense id][k] += word k of z_i h_i  (64-bit counters: at most 2^31 summands of 32 bits)
+__global__ void __launch_bounds__(256)
+k_key_accumulate(const uint32_t *__restrict__ zh, const uint32_t *__restrict__ rep, const uint32_t *__restrict__ dense, size_t n,
+                 unsigned long long *__restrict__ acc)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long *a = acc + 8 * (size_t)dense[rep[i]];
 #pragma unroll
-    for (int k = 0; k < 6; k++) dst[k] = src[k];
+    for (int k = 0; k < 8; k++) atomicAdd(a + k, (unsigned long long)zh[8 * i + k]);
+}
+
+// carry the eight counters of a key into one integer (< 2^287) and reduce it mod l
+__global__ void k_key_finalize(const unsigned long long *__restrict__ acc, size_t nkeys, uint32_t *__restrict__ out)
+{
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nkeys) return;
+    uint32_t x[16];
+    unsigned long long carry = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        unsigned long long v = acc[8 * j + k];
+        unsigned long long lo = (v & 0xffffffffull) + (carry & 0xffffffffull);
+        x[k] = (uint32_t)lo;
+        carry = (v >> 32) + (carry >> 32) + (lo >> 32);
+    }
+    x[8] = (uint32_t)carry; x[9] = (uint32_t)(carry >> 32);
+#pragma unroll
+    for (int k = 10; k < 16; k++) x[k] = 0;
+    uint32_t r[8];
+    sc_reduce512(r, x);
+#pragma unroll
+    for (int k = 0; k < 8; k++) out[8 * j + k] = r[k];
 }
 
 // ------------------------------------------------------------------------------------------
+// MSM inputs: scalars/points [0] = (-sum z s, B); [1 .. 1+K) = the K distinct keys (K = n without merging);
+// [1+n .. 1+2n) = (z_i, R_i).  counters: [0] running number of distinct keys, [1+p] its value after piece p, [15] = 0.
 struct VerifyBufs { uint32_t *hrams, *hs, *zsprod, *zs, *scalars; ge_niels_packed *points; int *flags;
-                    uint32_t *table, tmask, *rep, *uniq, *uniq_count; };
+                    uint32_t *table, tmask, *rep, *uniq, *dense, *counters; };
 
 static int verify_reserve(dalek_b200_ctx *ctx, size_t n, VerifyBufs &b)
 {
@@ -285,15 +322,16 @@ static int verify_reserve(dalek_b200_ctx *ctx, size_t n, VerifyBufs &b)
     b.hrams = (uint32_t *)ctx->misc2.p; b.hs = (uint32_t *)ctx->misc3.p; b.zsprod = (uint32_t *)ctx->misc4.p;
     b.zs = (uint32_t *)ctx->zs.p; b.scalars = (uint32_t *)ctx->scalars.p; b.points = (ge_niels_packed *)ctx->points.p;
     b.flags = (int *)ctx->flags.p;
-    // key de-duplication table: power of two >= 2n slots, plus rep[n], uniq[n] and 4 piece counters
+    // key de-duplication table: power of two >= 2n slots, plus rep[n], uniq[n], dense[n] and 16 counters
     size_t tsize = 1024;
     while (tsize < 2 * n) tsize <<= 1;
-    if ((rc = ws_reserve(ctx, ctx->key_table, (tsize + 2 * std::max<size_t>(1, n) + 8) * 4))) return rc;
+    const size_t n1 = std::max<size_t>(1, n);
+    if ((rc = ws_reserve(ctx, ctx->key_table, (tsize + 3 * n1 + 16) * 4))) return rc;
     b.table = (uint32_t *)ctx->key_table.p; b.tmask = (uint32_t)(tsize - 1);
-    b.rep = b.table + tsize; b.uniq = b.rep + std::max<size_t>(1, n); b.uniq_count = b.uniq + std::max<size_t>(1, n);
+    b.rep = b.table + tsize; b.uniq = b.rep + n1; b.dense = b.uniq + n1; b.counters = b.dense + n1;
     if (ctx->opt_dedupe_keys) {
         CUDA_TRY(ctx, cudaMemsetAsync(b.table, 0xff, tsize * 4, ctx->stream));
-        CUDA_TRY(ctx, cudaMemsetAsync(b.uniq_count, 0, 32, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(b.counters, 0, 64, ctx->stream));
     }
     return 0;
 }
@@ -316,36 +354,36 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
         k_transcript<<<cdiv(nchunks, 64), 64, 0, st>>>(b.hrams + 16 * i0, d_sigs + 16 * i0, cnt, chunk, b.zs + 4 * i0);
         ctx->launches += 2;
     }
-    ge_niels_packed *points_A = b.points + 1 + n;
-    k_prep_R<<<cdiv(cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, cnt, b.points + 1 + i0, i0 == 0 ? b.points : nullptr, b.flags);
+    ge_niels_packed *points_A = b.points + 1;
+    k_prep_R<<<cdiv(cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, cnt, b.points + 1 + n + i0, i0 == 0 ? b.points : nullptr, b.flags);
     ctx->launches++;
-    if (cnt) {
-        if (ctx->opt_dedupe_keys) {
-            uint32_t *uc = b.uniq_count + piece, *ul = b.uniq + i0;      // this piece's list of representatives
-            k_key_dedupe<<<cdiv(cnt, 256), 256, 0, st2>>>(d_keys, i0, cnt, b.table, b.tmask, b.rep, ul, uc);
-            k_prep_A<<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, ul, uc, i0, cnt, points_A, b.flags);
-            k_copy_A<<<cdiv(cnt, 256), 256, 0, st2>>>(b.rep, i0, cnt, points_A);
-            ctx->launches += 3;
-        } else {
-            k_prep_A<<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, nullptr, nullptr, i0, cnt, points_A, b.flags);
-            ctx->launches++;
-        }
+    if (ctx->opt_dedupe_keys) {
+        // keys first seen in this piece are uniq[counters[piece] .. counters[1 + piece])  (counters[15] = 0 for piece 0)
+        const uint32_t *lo = piece ? b.counters + piece : b.counters + 15, *hi = b.counters + 1 + piece;
+        if (cnt) k_key_dedupe<<<cdiv(cnt, 256), 256, 0, st2>>>(d_keys, i0, cnt, b.table, b.tmask, b.rep, b.uniq, b.dense, b.counters);
+        CUDA_TRY(ctx, cudaMemcpyAsync(b.counters + 1 + piece, b.counters, 4, cudaMemcpyDeviceToDevice, st2));
+        if (cnt) k_prep_A<<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, b.uniq, lo, hi, i0, cnt, points_A, b.flags);
+        ctx->launches += cnt ? 2 : 0;
+    } else if (cnt) {
+        k_prep_A<<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, nullptr, nullptr, nullptr, i0, cnt, points_A, b.flags);
+        ctx->launches++;
     }
     if (cnt) {
-        k_coeffs<<<cdiv(cnt, 128), 128, 0, st>>>(b.zs + 4 * i0, d_sigs + 16 * i0, b.hs + 8 * i0, cnt, b.scalars + 8 * (1 + i0),
-                                                 b.scalars + 8 * (1 + n + i0), b.zsprod + 8 * i0);
+        // with key merging z_i h_i replaces h_i in place and is summed per key in verify_tail
+        uint32_t *out_zh = ctx->opt_dedupe_keys ? b.hs + 8 * i0 : b.scalars + 8 * (1 + i0);
+        k_coeffs<<<cdiv(cnt, 128), 128, 0, st>>>(b.zs + 4 * i0, d_sigs + 16 * i0, b.hs + 8 * i0, cnt, b.scalars + 8 * (1 + n + i0),
+                                                 out_zh, b.zsprod + 8 * i0);
         ctx->launches++;
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
 
-// -sum z_i s_i, the (2n+1)-term MSM (batch.rs:240-244) and the verdict
-static int verify_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n)
+// -sum z_i s_i, the per-key scalars, the MSM (batch.rs:240-244) and the verdict
+static int verify_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, int pieces)
 {
     int rc;
     cudaStream_t st = ctx->stream, st2 = ctx->stream2;
-    const size_t m = 2 * n + 1;
     const uint32_t nsum = 32768;
     k_sum_partial<<<cdiv(nsum, 128), 128, 0, st>>>(b.zsprod, n, nsum, (uint32_t *)ctx->misc5.p);
     k_sum_final<<<1, 256, 0, st>>>((const uint32_t *)ctx->misc5.p, nsum, b.scalars);
@@ -353,12 +391,35 @@ static int verify_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n)
     ctx->last_zs_n = n;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, st2));
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
-    int c = msm_choose_window_bits(ctx, m);
-    int nwin = msm_window_count_for_bits(c);
+    if ((rc = pinned_reserve(ctx, sizeof(MsmResult) + 128))) return rc;
+    size_t nkeys = n;
+    if (ctx->opt_dedupe_keys && n) {
+        // the number of distinct keys sizes the MSM: one small read-back in the middle of the call
+        uint32_t *hk = (uint32_t *)((char *)ctx->h_pinned + sizeof(MsmResult) + 64);
+        CUDA_TRY(ctx, cudaMemcpyAsync(hk, b.counters + pieces, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        nkeys = *hk;
+        if (nkeys == 0 || nkeys > n) { ctx->last_error = "key table corrupted"; return -4; }
+        if (nkeys == n) {
+            k_key_gather<<<cdiv(n, 256), 256, 0, st>>>(b.hs, b.uniq, n, b.scalars + 8);
+            ctx->launches++;
+        } else {
+            if ((rc = ws_reserve(ctx, ctx->key_acc, nkeys * 64))) return rc;
+            unsigned long long *acc = (unsigned long long *)ctx->key_acc.p;
+            CUDA_TRY(ctx, cudaMemsetAsync(acc, 0, nkeys * 64, st));
+            k_key_accumulate<<<cdiv(n, 256), 256, 0, st>>>(b.hs, b.rep, b.dense, n, acc);
+            k_key_finalize<<<cdiv(nkeys, 128), 128, 0, st>>>(acc, nkeys, b.scalars + 8);
+            ctx->launches += 2;
+        }
+    }
+    // the z_i are 128-bit (batch.rs:224-229): their terms only populate the low windows
+    const int c = msm_choose_window_bits_mixed(ctx, n, 128, nkeys + 1);
+    const int nwin = msm_window_count_for_bits(c);
     if ((rc = ws_reserve(ctx, ctx->misc0, (size_t)nwin * sizeof(ge_p3_raw)))) return rc;
     if ((rc = ws_reserve(ctx, ctx->result, sizeof(MsmResult)))) return rc;
-    if ((rc = msm_full(ctx, b.scalars, b.points, PK_NIELS, m, c, (ge_p3_raw *)ctx->misc0.p, (MsmResult *)ctx->result.p))) return rc;
-    if ((rc = pinned_reserve(ctx, sizeof(MsmResult) + 128))) return rc;
+    if ((rc = msm_accumulate_chunk(ctx, b.scalars, b.points, PK_NIELS, nkeys + 1, c, true))) return rc;
+    if (n && (rc = msm_accumulate_chunk(ctx, b.scalars + 8 * (1 + n), b.points + 1 + n, PK_NIELS, n, c, false, (128 + c) / c))) return rc;
+    if ((rc = msm_reduce_finish(ctx, c, (ge_p3_raw *)ctx->misc0.p, (MsmResult *)ctx->result.p))) return rc;
     MsmResult *h = (MsmResult *)ctx->h_pinned;
     int *hflags = (int *)((char *)ctx->h_pinned + sizeof(MsmResult));
     CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->result.p, sizeof(MsmResult), cudaMemcpyDeviceToHost, st));
@@ -383,7 +444,7 @@ static int verify_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t
     CUDA_TRY(ctx, cudaMemsetAsync(b.flags, 0, 64, ctx->stream));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     if ((rc = verify_front(ctx, b, d_msgs, d_offs, d_sigs, d_keys, n, 0, n, ctx->ev_fork))) return rc;
-    return verify_tail(ctx, b, n);
+    return verify_tail(ctx, b, n, 1);
 }
 
 extern "C" {
@@ -436,7 +497,7 @@ int ed25519_b200_verify_batch_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_grp[k], sc));
         if ((rc = verify_front(ctx, b, d_msgs, d_offs, (const uint32_t *)d_sigs, (const uint32_t *)d_keys, n, i0, i1, ctx->ev_grp[k], k))) return rc;
     }
-    return verify_tail(ctx, b, n);
+    return verify_tail(ctx, b, n, K);
 }
 
 int ed25519_b200_verify_batch(dalek_b200_ctx *ctx, const uint8_t *const *msgs, const size_t *msg_lens,

@@ -37,7 +37,7 @@ struct dalek_b200_ctx {
     int last_kernel_launches = 0;
     // device workspaces (grown on demand, reused across calls)
     DevBuf scalars, points_in, points, digits, counts, offsets, sorted, buckets, red_a, red_b, red_c,
-        red_d, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums, msg_offs, sum_desc, sum_part, key_table;
+        red_d, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums, msg_offs, sum_desc, sum_part, key_table, key_acc;
     int sum_desc_c = -1;
     bool base_table_ready = false;
     // pinned host staging
@@ -80,7 +80,9 @@ int msm_window_sums(dalek_b200_ctx *ctx, const uint32_t *d_scalars /* n x 8 word
 struct MsmResult { uint32_t compressed[8]; uint64_t limbs[20]; uint32_t is_identity; uint32_t pad; };
 // building blocks: one chunk of pairs into the buckets; then reduction (+ Horner + encode if d_result)
 int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n,
-                         int c, bool first);
+                         int c, bool first, int active_windows = 0);
+// window width for `n_short` scalars of `short_bits` bits plus `n_long` full-width scalars (verify_batch)
+int msm_choose_window_bits_mixed(const dalek_b200_ctx *ctx, size_t n_short, int short_bits, size_t n_long);
 int msm_reduce_finish(dalek_b200_ctx *ctx, int c, ge_p3_raw *d_windows, MsmResult *d_result);
 // window sums + Horner + encode in one go (single-shard case)
 int msm_full(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n, int c,

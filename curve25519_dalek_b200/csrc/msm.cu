@@ -121,6 +121,20 @@ int msm_choose_window_bits(const dalek_b200_ctx *ctx, size_t n)
     return best;
 }
 
+// The same cost model when `n_short` scalars have only `short_bits` bits: they contribute ceil((bits+1)/c)
+// bucket additions each (one spare bit for the signed-digit carry).
+int msm_choose_window_bits_mixed(const dalek_b200_ctx *ctx, size_t n_short, int short_bits, size_t n_long)
+{
+    if (ctx->opt_window_bits >= 4 && ctx->opt_window_bits <= 20) return (int)ctx->opt_window_bits;
+    int best = 4; double best_cost = 1e300;
+    for (int c = 4; c <= 20; c++) {
+        double W = (double)((253 + c - 1) / c), Ws = (double)((short_bits + 1 + c - 1) / c);
+        double cost = Ws * (double)n_short + W * ((double)n_long + 4.0 * (double)(1u << (c - 1)));
+        if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+}
+
 // ------------------------------------------------------------------------------------------
 // digits + histogram.  entry = (int32 digit << 32) | rank
 __global__ void k_digits(const uint4 *__restrict__ scalars, size_t n, int c, int nwin, uint32_t nbuckets,
@@ -573,15 +587,18 @@ k_combine(const ge_p3_raw *__restrict__ windows, int ranks, int nwin, int c, Msm
 // One chunk of (scalar, point) pairs: digits, counting sort, task lists and bucket accumulation.
 // `first` chunks start the buckets at the identity; later chunks add onto them.  All chunks of one
 // MSM must use the same window width c.
+// `active_windows` > 0 promises that every scalar of this chunk is below 2^(c * active_windows - 1): digits are
+// extracted, sorted and accumulated for the low `active_windows` windows only (verify_batch: the 128-bit z_i).
 int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n,
-                         int c, bool first)
+                         int c, bool first, int active_windows)
 {
     const int nwin = msm_window_count_for_bits(c);
+    const int nact = active_windows > 0 && active_windows < nwin ? active_windows : nwin;
     const uint32_t nb = 1u << (c - 1);
     const size_t total_buckets = (size_t)nwin * nb;
-    const uint32_t task_len = msm_task_len(n, nwin, nb);
-    const size_t max_tasks = total_buckets + (std::max<size_t>(1, n) * nwin) / task_len + 1;
-    const size_t max_heavy = (std::max<size_t>(1, n) * nwin) / task_len + 1;
+    const uint32_t task_len = msm_task_len(n, nact, nb);
+    const size_t max_tasks = total_buckets + (std::max<size_t>(1, n) * nact) / task_len + 1;
+    const size_t max_heavy = (std::max<size_t>(1, n) * nact) / task_len + 1;
     const uint32_t parts = (nb + SCAN_PART - 1) / SCAN_PART;
     cudaStream_t st = ctx->stream;
     int rc;
@@ -592,8 +609,8 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
     if ((rc = ws_reserve(ctx, ctx->task_off, total_buckets * 4 + (nwin + 1) * 4))) return rc;
     if ((rc = ws_reserve(ctx, ctx->tasks, max_tasks * 8))) return rc;
     if ((rc = ws_reserve(ctx, ctx->task_sums, max_tasks * sizeof(ge_p3_raw)))) return rc;
-    if ((rc = ws_reserve(ctx, ctx->digits, std::max<size_t>(1, n) * nwin * 8))) return rc;
-    if ((rc = ws_reserve(ctx, ctx->sorted, std::max<size_t>(1, n) * nwin * 4))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->digits, std::max<size_t>(1, n) * nact * 8))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->sorted, std::max<size_t>(1, n) * nact * 4))) return rc;
     if ((rc = ws_reserve(ctx, ctx->buckets, total_buckets * sizeof(ge_p3_raw)))) return rc;
     uint32_t *counts = (uint32_t *)ctx->counts.p, *offsets = (uint32_t *)ctx->offsets.p;
     uint32_t *ntasks = (uint32_t *)ctx->ntasks.p, *task_off = (uint32_t *)ctx->task_off.p;
@@ -608,7 +625,7 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
 
     CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (total_buckets + 1) * 4, st));
     if (n) {
-        k_digits<<<cdiv(n, 256), 256, 0, st>>>((const uint4 *)d_scalars, n, c, nwin, nb, counts, entries);
+        k_digits<<<cdiv(n, 256), 256, 0, st>>>((const uint4 *)d_scalars, n, c, nact, nb, counts, entries);
         ctx->launches++;
     }
     k_scan_partial<<<nwin * parts, 1024, 0, st>>>(counts, nb, parts, part_sums);
@@ -622,9 +639,9 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
     k_task_fill<<<cdiv(total_buckets, 256), 256, 0, st>>>(ntasks, task_off, win_base, nb, (uint32_t)total_buckets, tasks);
     ctx->launches += 9;
     if (n) {
-        const int wg = (int)std::max<size_t>(1, std::min<size_t>((size_t)nwin, ((size_t)64 << 20) / (n * 4)));
-        for (int w0 = 0; w0 < nwin; w0 += wg) {
-            k_scatter<<<cdiv(n, 256), 256, 0, st>>>(entries, offsets, n, w0, std::min(nwin, w0 + wg), nb, sorted);
+        const int wg = (int)std::max<size_t>(1, std::min<size_t>((size_t)nact, ((size_t)64 << 20) / (n * 4)));
+        for (int w0 = 0; w0 < nact; w0 += wg) {
+            k_scatter<<<cdiv(n, 256), 256, 0, st>>>(entries, offsets, n, w0, std::min(nact, w0 + wg), nb, sorted);
             ctx->launches++;
         }
     }

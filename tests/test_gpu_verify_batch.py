@@ -198,3 +198,24 @@ def test_verify_batch_key_dedupe(eng, oracle):
             z1 = zs
         else:
             assert zs == z1
+
+
+def test_verify_batch_key_merging_edges(eng, oracle):
+    """One MSM term per distinct key (scalar = sum of z_i h_i over its signatures): n-1 distinct keys (a single
+    merged pair), every signature under one key, and a swap of two signatures of the same key (each valid for the
+    other's message only) must all give the oracle's verdict."""
+    msgs, sigs, pks = make_batch(oracle, 150, seed=901)
+    rnd = random.Random(902)
+    sk = rnd.randbytes(32)
+    msgs[77] = b"second message of key 3"; pks[77] = pks[3]
+    # signature 77 must really be by key 3: rebuild both from one seed
+    pks[3] = pks[77] = oracle.public_key(sk)
+    sigs[3], sigs[77] = oracle.sign(msgs[3], sk), oracle.sign(msgs[77], sk)
+    assert run(eng, msgs, sigs, pks) == OK == oracle.verify_batch(msgs, sigs, pks, chunk=128)
+    swapped = list(sigs); swapped[3], swapped[77] = sigs[77], sigs[3]
+    assert run(eng, msgs, swapped, pks) == VERIFY == oracle.verify_batch(msgs, swapped, pks, chunk=128)
+    one_key = [oracle.public_key(sk)] * 150
+    one_sigs = [oracle.sign(m, sk) for m in msgs]
+    assert run(eng, msgs, one_sigs, one_key) == OK
+    bad = list(one_sigs); x = bytearray(bad[149]); x[2] ^= 0x10; bad[149] = bytes(x)      # R of the last signature
+    assert run(eng, msgs, bad, one_key) == VERIFY == oracle.verify_batch(msgs, bad, one_key, chunk=128)
