@@ -61,7 +61,8 @@ const char *dalek_b200_last_error(const dalek_b200_ctx *ctx);
  * (signatures per transcript, default 128; see verify_batch below), "field_f64" (1 = bucket kernel
  * on the FP64-pipe field, default; 0 = IMAD.WIDE field), "host_chunks" (1..4, host-buffer MSM calls
  * stream their input in this many chunks, default 2), "verify_pieces" (1..4, same for verify_batch,
- * default 4), "dedupe_keys" (1 = decompress every distinct public key once, default).
+ * default 4), "dedupe_keys" (1 = decompress every distinct public key once and give it one MSM term,
+ * default), "double_base_comb" (1 = fixed-base comb for double-base batches of >= 4096 pairs, default).
  * Returns 0 or DALEK_E_INVALID_ARG. */
 int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
@@ -122,7 +123,11 @@ int dalek_b200_edwards_msm_combine(dalek_b200_ctx *ctx, const uint64_t *windows,
 /* n independent RistrettoPoint::multiscalar_mul([a_i, b_i], [G, H]) (constant-time Straus,
  * C/ristretto.rs:964-977 -> C/edwards.rs:970-995 -> straus.rs:103-144), each result compressed
  * (RistrettoPoint::compress, C/ristretto.rs:500-533).  G, H: CompressedRistretto; a, b: n x 32 B.
- * out: n x 32 B.  Returns DALEK_NONE if G or H does not decode (C/ristretto.rs:266-345). */
+ * out: n x 32 B.  Returns DALEK_NONE if G or H does not decode (C/ristretto.rs:266-345; `out` is then
+ * unspecified), DALEK_E_INVALID_ARG for a scalar with bit 255 set.  The results are those of the
+ * reference's Straus; batches of >= 4096 pairs are computed with a fixed-base comb over tables of G
+ * and H (same constant-time discipline: masked full-row scans, uniform control flow).  Pinned host
+ * buffers let the copies overlap the arithmetic. */
 int dalek_b200_ristretto_double_base_batch(dalek_b200_ctx *ctx, const uint8_t *a, const uint8_t *b,
                                            const uint8_t G[32], const uint8_t H[32], size_t n,
                                            uint8_t *out);

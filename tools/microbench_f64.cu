@@ -194,6 +194,28 @@ __global__ void __launch_bounds__(128) k_rate(uint64_t *out, const uint32_t *in)
     out[64 + blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// MODE 6 family: squarings on both pipes at once.  Of every 4 warps, IW run the integer squaring (IMAD.WIDE on
+// the FMA pipe) for ITERS * PCT / 100 iterations and the others the FP64 squaring for ITERS iterations.
+template <int IW, int PCT>
+__global__ void __launch_bounds__(128) k_mix_sq(uint64_t *out, const uint32_t *in)
+{
+    fe a, b;
+    for (int i = 0; i < 10; i++) { a.v[i] = in[i] + threadIdx.x; b.v[i] = in[10 + i] ^ (blockIdx.x & 0xff); }
+    fe_carry(a, a); fe_carry(b, b);
+    uint64_t s = 0;
+    if ((int)((threadIdx.x >> 5) & 3) < IW) {
+#pragma unroll 1
+        for (int i = 0; i < ITERS * PCT / 100; i++) { fe_sq(a, a); fe_sq(b, b); }
+        for (int i = 0; i < 10; i++) s ^= a.v[i] ^ b.v[i];
+    } else {
+        fe64 x, y; fe64_from_fe(x, a); fe64_from_fe(y, b);
+#pragma unroll 1
+        for (int i = 0; i < ITERS; i++) { fe64_sq_v2(x, x); fe64_sq_v2(y, y); }
+        for (int i = 0; i < 5; i++) s ^= (uint64_t)__double_as_longlong(x.v[i]) ^ (uint64_t)__double_as_longlong(y.v[i]);
+    }
+    out[64 + blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F> static float time_ms(F launch, int reps = 5)
 {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -223,6 +245,13 @@ int main()
         ms = time_ms([&] { k_rate<4><<<blocks, threads>>>(out, in); }); printf(", \"int_sq_G_b%d\": %.1f", bps, n / (ms * 1e-3) / 1e9);
         ms = time_ms([&] { k_rate<3><<<blocks, threads>>>(out, in); }); printf(", \"f64_sq_G_b%d\": %.1f", bps, n / (ms * 1e-3) / 1e9);
         ms = time_ms([&] { k_rate<5><<<blocks, threads>>>(out, in); }); printf(", \"mixed_int_f64_mul_G_b%d\": %.1f", bps, n / (ms * 1e-3) / 1e9);
+    }
+    for (int bps : {4, 8}) {
+        int blocks = sms * bps, threads = 128; float ms;
+#define MIX(IW, PCT) ms = time_ms([&] { k_mix_sq<IW, PCT><<<blocks, threads>>>(out, in); }); \
+        printf(", \"mix_sq_iw%d_pct%d_G_b%d\": %.1f", IW, PCT, bps, (double)blocks * 32 * 2 * (IW * (ITERS * PCT / 100) + (4 - IW) * ITERS) / (ms * 1e-3) / 1e9);
+        MIX(1, 50) MIX(1, 100) MIX(1, 150) MIX(2, 50) MIX(2, 75) MIX(2, 100) MIX(3, 50) MIX(3, 100)
+#undef MIX
     }
     printf("}\n");
     return 0;
