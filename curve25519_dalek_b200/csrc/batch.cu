@@ -172,7 +172,11 @@ __global__ void k_sum_final(const uint32_t *__restrict__ partial, uint32_t count
 
 // decompress R_i (first half of each signature) of `cnt` signatures into out_R = &points[1 + i0];
 // thread cnt writes the basepoint into out_B (slot 0) when given
-__global__ void __launch_bounds__(128)
+#ifndef PREP_MIN_BLOCKS
+#define PREP_MIN_BLOCKS 3
+#endif
+template <int F64>
+__global__ void __launch_bounds__(128, PREP_MIN_BLOCKS)
 k_prep_R(const uint32_t *__restrict__ sigs, size_t cnt, ge_niels_packed *__restrict__ out_R, ge_niels_packed *__restrict__ out_B,
          int *__restrict__ flags)
 {
@@ -188,7 +192,7 @@ k_prep_R(const uint32_t *__restrict__ sigs, size_t cnt, ge_niels_packed *__restr
 #pragma unroll
         for (int k = 0; k < 8; k++) s[k] = sigs[16 * j + k];
         dst = out_R + j;
-        if (!ge_decompress_affine(x, y, s)) { atomicOr(&flags[FLAG_BAD_R], 1); fe_0(x); fe_1(y); }
+        if (!ge_decompress_affine<F64>(x, y, s)) { atomicOr(&flags[FLAG_BAD_R], 1); fe_0(x); fe_1(y); }
     }
     ge_niels nl; ge_affine_to_niels(nl, x, y);
     ge_niels_packed p; ge_niels_pack(p, nl);
@@ -236,7 +240,8 @@ k_key_dedupe(const uint32_t *__restrict__ keys /* all n keys */, size_t i0, size
 
 // decompress the keys listed in uniq[*lo .. *hi) into points_A[position] (or, without a list, keys
 // i0 .. i0+cnt into points_A[index])
-__global__ void __launch_bounds__(128)
+template <int F64>
+__global__ void __launch_bounds__(128, PREP_MIN_BLOCKS)
 k_prep_A(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ uniq, const uint32_t *__restrict__ lo,
          const uint32_t *__restrict__ hi, size_t i0, size_t cnt, ge_niels_packed *__restrict__ points_A, int *__restrict__ flags)
 {
@@ -247,7 +252,7 @@ k_prep_A(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ uniq, c
 #pragma unroll
     for (int k = 0; k < 8; k++) s[k] = keys[8 * i + k];
     fe x, y;
-    if (!ge_decompress_affine(x, y, s)) { atomicOr(&flags[FLAG_BAD_A], 1); fe_0(x); fe_1(y); }
+    if (!ge_decompress_affine<F64>(x, y, s)) { atomicOr(&flags[FLAG_BAD_A], 1); fe_0(x); fe_1(y); }
     ge_niels nl; ge_affine_to_niels(nl, x, y);
     ge_niels_packed p; ge_niels_pack(p, nl);
     uint4 *o = reinterpret_cast<uint4 *>(points_A + slot);
@@ -355,17 +360,22 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
         ctx->launches += 2;
     }
     ge_niels_packed *points_A = b.points + 1;
-    k_prep_R<<<cdiv(cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, cnt, b.points + 1 + n + i0, i0 == 0 ? b.points : nullptr, b.flags);
+    if (ctx->opt_decompress_f64)
+        k_prep_R<1><<<cdiv(cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, cnt, b.points + 1 + n + i0, i0 == 0 ? b.points : nullptr, b.flags);
+    else
+        k_prep_R<0><<<cdiv(cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, cnt, b.points + 1 + n + i0, i0 == 0 ? b.points : nullptr, b.flags);
     ctx->launches++;
     if (ctx->opt_dedupe_keys) {
         // keys first seen in this piece are uniq[counters[piece] .. counters[1 + piece])  (counters[15] = 0 for piece 0)
         const uint32_t *lo = piece ? b.counters + piece : b.counters + 15, *hi = b.counters + 1 + piece;
         if (cnt) k_key_dedupe<<<cdiv(cnt, 256), 256, 0, st2>>>(d_keys, i0, cnt, b.table, b.tmask, b.rep, b.uniq, b.dense, b.counters);
         CUDA_TRY(ctx, cudaMemcpyAsync(b.counters + 1 + piece, b.counters, 4, cudaMemcpyDeviceToDevice, st2));
-        if (cnt) k_prep_A<<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, b.uniq, lo, hi, i0, cnt, points_A, b.flags);
+        if (cnt && ctx->opt_decompress_f64) k_prep_A<1><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, b.uniq, lo, hi, i0, cnt, points_A, b.flags);
+        else if (cnt) k_prep_A<0><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, b.uniq, lo, hi, i0, cnt, points_A, b.flags);
         ctx->launches += cnt ? 2 : 0;
     } else if (cnt) {
-        k_prep_A<<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, nullptr, nullptr, nullptr, i0, cnt, points_A, b.flags);
+        if (ctx->opt_decompress_f64) k_prep_A<1><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, nullptr, nullptr, nullptr, i0, cnt, points_A, b.flags);
+        else k_prep_A<0><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, nullptr, nullptr, nullptr, i0, cnt, points_A, b.flags);
         ctx->launches++;
     }
     if (cnt) {

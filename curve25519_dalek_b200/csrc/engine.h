@@ -31,6 +31,7 @@ struct dalek_b200_ctx {
     long opt_double_base_comb = 1; // double-base batch through the shared-memory fixed-base comb (0 = per-pair Straus)
     long opt_dedupe_keys = 1;   // verify_batch decompresses every distinct public key once
     long opt_verify_pieces = 4; // host-buffer verify_batch calls stream the signatures in this many pieces
+    long opt_decompress_f64 = 1; // square-root exponentiation of point decompression on the FP64-pipe field
     long opt_field_f64 = 1;     // bucket kernel on the FP64 pipe (fe64.cuh) instead of IMAD.WIDE (fe.cuh)
     // timing of the dominant kernel in the last call
     float last_kernel_ms = 0.f;

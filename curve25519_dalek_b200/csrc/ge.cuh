@@ -9,6 +9,7 @@
 #pragma once
 #include "constants.cuh"
 #include "fe.cuh"
+#include "fe64.cuh"
 
 struct ge_p3 { fe X, Y, Z, T; };           // EdwardsPoint (extended), all scale 1
 struct ge_p2 { fe X, Y, Z; };              // ProjectivePoint
@@ -165,13 +166,16 @@ FE_HD void ge_affine_to_niels(ge_niels &r, const fe &x, const fe &y)
 }
 
 // sqrt_ratio_i (C/field.rs:320-366): returns was_nonzero_square, r = nonnegative root
+// F64 = 1 runs the 252-squaring exponentiation on the FP64-pipe field (fe64.cuh): same value, faster on B200.
+template <int F64 = 0>
 FE_HD uint32_t fe_sqrt_ratio_i(fe &r, const fe &u, const fe &v)
 {
     fe v3, v7, t, check, i, neg_u, neg_u_i, r_prime;
     fe_const_sqrtm1(i);
     fe_sq(t, v); fe_mul(v3, t, v);
     fe_sq(t, v3); fe_mul(v7, t, v);
-    fe_mul(t, u, v7); fe_pow_p58(t, t);
+    fe_mul(t, u, v7);
+    if (F64) fe_pow_p58_f64(t, t); else fe_pow_p58(t, t);
     fe_mul(r, u, v3); fe_mul(r, r, t);
     fe_sq(t, r); fe_mul(check, v, t);
     fe uc; fe_carry(uc, u);
@@ -190,6 +194,7 @@ FE_HD uint32_t fe_sqrt_ratio_i(fe &r, const fe &u, const fe &v)
 
 // CompressedEdwardsY::decompress (C/edwards.rs:211-257).  s = 8 little-endian words.
 // Returns 1 and affine (x, y) on success.  Accepts non-canonical y like the reference.
+template <int F64 = 0>
 FE_HD uint32_t ge_decompress_affine(fe &x, fe &y, const uint32_t s[8])
 {
     fe one, YY, u, v, d;
@@ -198,7 +203,7 @@ FE_HD uint32_t ge_decompress_affine(fe &x, fe &y, const uint32_t s[8])
     fe_sq(YY, y);
     fe_sub(u, YY, one);                      // 3
     fe_mul(v, YY, d); fe_add(v, v, one);     // ~1
-    uint32_t ok = fe_sqrt_ratio_i(x, u, v);
+    uint32_t ok = fe_sqrt_ratio_i<F64>(x, u, v);
     fe_cneg(x, s[7] >> 31);
     fe_carry(x, x);
     return ok;
@@ -276,6 +281,7 @@ FE_HD void fe_to_limbs51(uint64_t l[5], const fe &f)
 
 // CompressedRistretto::decompress (ristretto.rs:266-345).  Returns 1 and an extended point with
 // Z = 1 on success.
+template <int F64 = 0>
 FE_HD uint32_t ristretto_decompress(ge_p3 &p, const uint32_t in[8])
 {
     fe s, one, ss, u1, u2, u2_sqr, v, t, I, Dx, Dy, x, y, nd, d;
@@ -295,7 +301,7 @@ FE_HD uint32_t ristretto_decompress(ge_p3 &p, const uint32_t in[8])
     fe_sq(t, u1); fe_mul(t, nd, t);
     fe_sub(v, t, u2_sqr);                            // a d u1^2 - u2^2
     fe_mul(t, v, u2_sqr);
-    uint32_t ok = fe_sqrt_ratio_i(I, one, t);        // invsqrt (C/field.rs:380-382)
+    uint32_t ok = fe_sqrt_ratio_i<F64>(I, one, t);   // invsqrt (C/field.rs:380-382)
     fe_mul(Dx, I, u2);
     fe_mul(t, v, Dx); fe_mul(Dy, I, t);
     fe_add(t, s, s); fe_mul(x, t, Dx);
@@ -308,6 +314,7 @@ FE_HD uint32_t ristretto_decompress(ge_p3 &p, const uint32_t in[8])
 }
 
 // RistrettoPoint::compress (ristretto.rs:500-533)
+template <int F64 = 0>
 FE_HD void ristretto_compress(uint32_t out[8], const ge_p3 &p)
 {
     fe X = p.X, Y = p.Y, u1, u2, t, t2, I, i1, i2, z_inv, den_inv, iX, iY, ench, sm1, magic, s, one;
@@ -315,7 +322,7 @@ FE_HD void ristretto_compress(uint32_t out[8], const ge_p3 &p)
     fe_add(t, p.Z, Y); fe_sub(t2, p.Z, Y); fe_mul(u1, t2, t);     // (Z+Y)(Z-Y)
     fe_mul(u2, X, Y);
     fe_sq(t, u2); fe_mul(t, u1, t);
-    (void)fe_sqrt_ratio_i(I, one, t);
+    (void)fe_sqrt_ratio_i<F64>(I, one, t);
     fe_mul(i1, I, u1);
     fe_mul(i2, I, u2);
     fe_mul(t, i2, p.T); fe_mul(z_inv, i1, t);

@@ -58,7 +58,8 @@ int pinned_reserve(dalek_b200_ctx *ctx, size_t bytes)
 
 // ------------------------------------------------------------------------------------------
 // point preparation
-__global__ void k_prep_compressed(const uint4 *__restrict__ in, ge_niels_packed *__restrict__ out, size_t n,
+template <int F64>
+__global__ void __launch_bounds__(128, 3) k_prep_compressed(const uint4 *__restrict__ in, ge_niels_packed *__restrict__ out, size_t n,
                                   int *__restrict__ bad)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,7 +67,7 @@ __global__ void k_prep_compressed(const uint4 *__restrict__ in, ge_niels_packed 
     uint4 a = in[2 * i], b = in[2 * i + 1];
     uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     fe x, y;
-    uint32_t ok = ge_decompress_affine(x, y, s);
+    uint32_t ok = ge_decompress_affine<F64>(x, y, s);
     if (!ok) { atomicOr(bad, 1); fe_0(x); fe_1(y); }   // identity placeholder keeps the kernels total
     ge_niels nl; ge_affine_to_niels(nl, x, y);
     ge_niels_packed p; ge_niels_pack(p, nl);
@@ -96,7 +97,8 @@ int msm_prepare_points(dalek_b200_ctx *ctx, const void *d_in, int point_fmt, siz
 {
     if (n == 0) return 0;
     if (point_fmt == DALEK_POINTS_COMPRESSED) {
-        k_prep_compressed<<<cdiv(n, 128), 128, 0, ctx->stream>>>((const uint4 *)d_in, (ge_niels_packed *)d_out, n, d_bad);
+        if (ctx->opt_decompress_f64) k_prep_compressed<1><<<cdiv(n, 128), 128, 0, ctx->stream>>>((const uint4 *)d_in, (ge_niels_packed *)d_out, n, d_bad);
+        else k_prep_compressed<0><<<cdiv(n, 128), 128, 0, ctx->stream>>>((const uint4 *)d_in, (ge_niels_packed *)d_out, n, d_bad);
     } else {
         k_prep_extended<<<cdiv(n, 128), 128, 0, ctx->stream>>>((const uint64_t *)d_in, (ge_pniels_packed *)d_out, n);
     }

@@ -211,7 +211,7 @@ k_double_base(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, co
         ge_padd(Q, Q, sel, (uint32_t)(db[j] < 0));
     }
     uint32_t enc[8];
-    ristretto_compress(enc, Q);
+    ristretto_compress<1>(enc, Q);
 #pragma unroll
     for (int k = 0; k < 8; k++) out[8 * i + k] = enc[k];
 }
@@ -303,7 +303,7 @@ k_double_base_comb(const uint32_t *__restrict__ a, const uint32_t *__restrict__ 
     }
     ge_p3 Q; ge64_to_p3(Q, acc);
     uint32_t enc[8];
-    ristretto_compress(enc, Q);
+    ristretto_compress<1>(enc, Q);                                 // inverse square root on the FP64 field too
 #pragma unroll
     for (int k = 0; k < 8; k++) out[8 * i + k] = enc[k];
 }
@@ -386,6 +386,7 @@ int ristretto_double_base(dalek_b200_ctx *ctx, const uint8_t *d_a, const uint8_t
 // ------------------------------------------------------------------------------------------
 // Ristretto vartime MSM: decode with the Ristretto rules, then the Edwards bucket MSM; encode the
 // result with RistrettoPoint::compress (ristretto.rs:980-994).
+template <int F64>
 __global__ void k_prep_ristretto(const uint32_t *__restrict__ in, ge_pniels_packed *__restrict__ out, size_t n, int *__restrict__ bad)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -394,7 +395,7 @@ __global__ void k_prep_ristretto(const uint32_t *__restrict__ in, ge_pniels_pack
 #pragma unroll
     for (int k = 0; k < 8; k++) enc[k] = in[8 * i + k];
     ge_p3 P;
-    if (!ristretto_decompress(P, enc)) { atomicOr(bad, 1); ge_p3_identity(P); }
+    if (!ristretto_decompress<F64>(P, enc)) { atomicOr(bad, 1); ge_p3_identity(P); }
     ge_pniels pn; ge_p3_to_pniels(pn, P);
     ge_pniels_packed pk; ge_pniels_pack(pk, pn);
     out[i] = pk;
@@ -480,10 +481,13 @@ int dalek_b200_ristretto_double_base_batch(dalek_b200_ctx *ctx, const uint8_t *a
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
-    const size_t pieces = n >= (1u << 16) ? 8 : 1;
-    for (size_t k = 0; k < pieces; k++) {
-        const size_t lo = n * k / pieces, hi = n * (k + 1) / pieces, m = hi - lo;
-        if (!m) continue;
+    // piece size: two full waves of the comb kernel (one 384-thread CTA per SM), so that no piece ends in a
+    // partly filled wave; the per-pair Straus kernel has small CTAs and simply gets 8 pieces
+    size_t piece = n;
+    if (n >= (1u << 16)) piece = plan.variant == 1 ? (size_t)2 * ctx->sm_count * 384 : (n + 7) / 8;
+    size_t k = 0;
+    for (size_t lo = 0; lo < n; lo += piece, k++) {
+        const size_t m = std::min(piece, n - lo);
         cudaStream_t st = ss[k & 1];
         CUDA_TRY(ctx, cudaMemcpyAsync(d_a + 32 * lo, a + 32 * lo, 32 * m, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaMemcpyAsync(d_b + 32 * lo, b + 32 * lo, 32 * m, cudaMemcpyHostToDevice, st));
@@ -515,7 +519,8 @@ int dalek_b200_ristretto_vartime_msm(dalek_b200_ctx *ctx, const uint8_t *scalars
     if (n) {
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->points_in.p, points, n * 32, cudaMemcpyHostToDevice, st));
-        k_prep_ristretto<<<cdiv(n, 128), 128, 0, st>>>((const uint32_t *)ctx->points_in.p, (ge_pniels_packed *)ctx->points.p, n, (int *)ctx->flags.p);
+        if (ctx->opt_decompress_f64) k_prep_ristretto<1><<<cdiv(n, 128), 128, 0, st>>>((const uint32_t *)ctx->points_in.p, (ge_pniels_packed *)ctx->points.p, n, (int *)ctx->flags.p);
+        else k_prep_ristretto<0><<<cdiv(n, 128), 128, 0, st>>>((const uint32_t *)ctx->points_in.p, (ge_pniels_packed *)ctx->points.p, n, (int *)ctx->flags.p);
         ctx->launches++;
     }
     int c = msm_choose_window_bits(ctx, n);

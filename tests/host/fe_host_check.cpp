@@ -94,6 +94,20 @@ void h_fe64_mul(uint8_t *o, const uint8_t *a, const uint8_t *b)
     fe64 S; fe64_add(S, Z, X); fe64_sub(S, S, Y); fe64_mul(Z, S, X);      // (a b^2 + a - b) a
     fe64_to_fe(z, Z); store(o, z);
 }
+// x^((p-5)/8) with the addition chain on the FP64 field (fe64_sq / fe64_mul host models, bound asserts on)
+void h_fe64_pow_p58(uint8_t *o, const uint8_t *a)
+{
+    fe x, z; load(x, a);
+    fe_pow_p58_f64(z, x); store(o, z);
+}
+void h_fe64_sq(uint8_t *o, const uint8_t *a, const uint8_t *b)
+{
+    fe x, y, z; load(x, a); load(y, b);
+    fe64 X, Y, S; fe64_from_fe(X, x); fe64_from_fe(Y, y);
+    fe64_sq(S, X); fe64_sq(S, S);                  // a^4
+    fe64_mul(S, S, Y); fe64_sq(S, S);              // (a^4 b)^2
+    fe64_to_fe(z, S); store(o, z);
+}
 // acc = sum_k (+/-) Q_k over `count` compressed points, alternating through madd / padd; returns compress(acc)
 int h_ge64_chain(uint8_t *out, const uint8_t *pts, const uint8_t *negs, int count)
 {

@@ -176,3 +176,39 @@ def test_msm_host_chunked_streaming(eng, oracle, fmt):
         finally:
             eng.set_option("host_chunks", 2)
         assert rc == 0 and got == want, chunks
+
+
+@pytest.mark.parametrize("f64", [1, 0])
+def test_decompress_edge_encodings(eng, oracle, kat, f64):
+    """CompressedEdwardsY::decompress (C/edwards.rs:211-257) inside the engine, with the square-root exponentiation
+    on either field: 1*P for edge encodings (non-canonical y, sign bit on x = 0, small order, non-squares) must
+    give the oracle's Option -- None, or the canonical re-encoding of the same point."""
+    p = pyref.p
+    rnd = random.Random(99)
+    encs = [y.to_bytes(32, "little") for y in (0, 1, 2, 3, 4, 5, p - 1, p, p + 1, p + 2, 2**255 - 1, 2**255 - 20, 2**254, 19)]
+    encs += [(y | (1 << 255)).to_bytes(32, "little") for y in (0, 1, p - 1, p, p + 1, 2**255 - 1, 4)]
+    encs += [bytes.fromhex(h) for h in (                      # order-8 points and their negatives
+        "26e8958fc2b227b045c3f489f2ef98f0d5dfac05d3c63339b13802886d53fc05", "26e8958fc2b227b045c3f489f2ef98f0d5dfac05d3c63339b13802886d53fc85",
+        "c7176a703d4dd84fba3c0b760d10670f2a2053fa2c39ccc64ec7fd7792ac037a", "c7176a703d4dd84fba3c0b760d10670f2a2053fa2c39ccc64ec7fd7792ac03fa")]
+    encs += [rnd.randbytes(32) for _ in range(60)]
+    one = (1).to_bytes(32, "little")
+    eng.set_option("decompress_f64", f64)
+    try:
+        n_none = 0
+        for e in encs:
+            q = oracle.decompress(e)
+            rc, got, _ = eng.edwards_vartime_msm(one, e, 1)
+            if q is None:
+                assert rc == 1, e.hex()
+                n_none += 1
+            else:
+                assert rc == 0 and got == oracle.compress(q), e.hex()
+        assert 10 < n_none < len(encs) - 10
+        # and all of the decodable ones in one call: sum_i (i+1) * P_i
+        good = [e for e in encs if oracle.decompress(e) is not None]
+        sc = [(i + 1).to_bytes(32, "little") for i in range(len(good))]
+        want = oracle.compress(oracle.msm("optional", sc, [oracle.decompress(e) for e in good]))
+        rc, got, _ = eng.edwards_vartime_msm(b"".join(sc), b"".join(good), len(good))
+        assert rc == 0 and got == want
+    finally:
+        eng.set_option("decompress_f64", 1)

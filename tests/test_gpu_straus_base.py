@@ -117,13 +117,14 @@ def test_ristretto_double_base_comb(eng, oracle, kat, variant):
 
 
 def test_ristretto_double_base_streamed_pieces(eng, oracle, kat):
-    """>= 2^16 pairs are streamed in 8 pieces over two streams: both kernels must agree everywhere and match
-    the oracle around every piece boundary and on a random sample."""
+    """>= 2^16 pairs are streamed in pieces over two streams (comb: two full waves = 2 * SMs * 384 pairs per piece;
+    Straus: 8 equal pieces): both kernels must agree everywhere and match the oracle around every piece boundary
+    and on a random sample."""
     import numpy as np
     G = bytes.fromhex(kat["constants"]["RISTRETTO_BASEPOINT_COMPRESSED"]["hex"])
     Gp = oracle.ristretto_decompress(G)
     Hc = oracle.ristretto_compress(oracle.scalarmul(b32(pyref.labelled_scalar(b"dalek-b200/H", 1, 0)), Gp))
-    n = 70001
+    n = 250001
     rng = np.random.Generator(np.random.PCG64(58))
     a = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); a[:, 31] &= 0x7F
     b = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); b[:, 31] &= 0x0F
@@ -136,7 +137,10 @@ def test_ristretto_double_base_streamed_pieces(eng, oracle, kat):
         outs.append(out.reshape(n, 32))
     eng.set_option("double_base_comb", 1)
     assert np.array_equal(outs[0], outs[1])
-    idx = sorted({min(n - 1, max(0, n * k // 8 + d)) for k in range(9) for d in (-1, 0, 1)} | set(rng.integers(0, n, size=150).tolist()))
+    import torch
+    wave2 = 2 * torch.cuda.get_device_properties(0).multi_processor_count * 384
+    idx = sorted({min(n - 1, max(0, b + d)) for b in [n * k // 8 for k in range(9)] + [wave2, 2 * wave2] for d in (-1, 0, 1)}
+                 | set(rng.integers(0, n, size=150).tolist()))
     rc, want = oracle.ristretto_double_base_batch(a[idx].tobytes(), b[idx].tobytes(), G, Hc)
     assert rc == 0 and outs[1][idx].tobytes() == want
     # a scalar with bit 255 set violates the Scalar invariant: rejected before any work
