@@ -333,7 +333,7 @@ def build_verify_inputs(eng, n, nkeys=1024):
     return flat, offs, np.frombuffer(sigs, dtype=np.uint8).copy(), np.frombuffer(pks, dtype=np.uint8).copy()
 
 
-def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkeys=1024):
+def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkeys=1024, batch_size=0):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -354,6 +354,12 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
 
     def step(host=False):
         b = h if host else d
+        if batch_size:      # independent batches of `batch_size`, one verdict each
+            rc, verdicts = eng.verify_batches_flat(b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(), n, batch_size,
+                                                   device_ptrs=not host)
+            if rc != 0 or any(verdicts):
+                raise SystemExit("bench: verify_batches rejected valid signatures")
+            return
         rc = eng.verify_batch_flat(b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(), n,
                                    device_ptrs=not host, msgs_bytes=n * 59)
         if rc != 0:
@@ -412,7 +418,7 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": el / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (radix 2^25.5), exact", "data": "synthetic: 59-byte messages, %d distinct keys, signatures made on the GPU (RFC 8032)" % min(nkeys, n),
         "config": {"workload": "ed25519_verify_batch", "signatures_per_gpu": n, "message_bytes": 59, "distinct_keys": min(nkeys, n),
-                   "verify_chunk": 128, "keys": "32-byte encodings, decompressed inside the call",
+                   "verify_chunk": 64, "keys": "32-byte encodings, decompressed inside the call",
                    "l2": "inputs (%.0f MB) exceed the 126 MB L2" % (n * 155 / 1e6),
                    "replicas": "independent batches per GPU, no collective" if world > 1 else "single batch"},
         "e2e": {"value": n * world * steps / et, "unit": "sigs/s", "h2d_bytes_per_step": n * 155 + (n + 1) * 8, "d2h_bytes_per_step": 192},
@@ -575,6 +581,9 @@ def main():
             # the same batch size with every public key different (no key de-duplication possible)
             v2 = run_verify(args, rank, world, local, eng=eng, steps=3, warmup=3, nkeys=1 << 30)
             line["verify_batch"]["all_distinct_keys"] = {k: v2[k] for k in ("value", "unit", "ms_per_step", "e2e")}
+            # the same signatures as 2^14 independent batches of 256 (per-batch verdicts, one reference transcript each)
+            v3 = run_verify(args, rank, world, local, eng=eng, steps=3, warmup=3, batch_size=256)
+            line["verify_batch"]["batches_of_256"] = {k: v3[k] for k in ("value", "unit", "ms_per_step", "e2e")}
             line["ristretto_double_base"] = run_double_base(eng)
     if rank == 0 and world == 1 and not args.no_extras:
         threads = 1

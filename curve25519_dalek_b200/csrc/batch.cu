@@ -29,7 +29,7 @@ enum { FLAG_BAD_A = 0, FLAG_BAD_S = 1, FLAG_BAD_R = 2 };
 __global__ void __launch_bounds__(128)
 k_hram(const uint8_t *__restrict__ msgs, const uint64_t *__restrict__ offs, const uint32_t *__restrict__ sigs,
        const uint32_t *__restrict__ keys, size_t n, uint32_t *__restrict__ hrams, uint32_t *__restrict__ hs,
-       int *__restrict__ flags)
+       int *__restrict__ flags, uint8_t *__restrict__ bad_s)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -50,7 +50,7 @@ k_hram(const uint8_t *__restrict__ msgs, const uint64_t *__restrict__ offs, cons
     sc_reduce512(h, dig);
 #pragma unroll
     for (int k = 0; k < 8; k++) hs[8 * i + k] = h[k];
-    if (!sc_is_canonical(s)) atomicOr(&flags[FLAG_BAD_S], 1);
+    if (!sc_is_canonical(s)) { atomicOr(&flags[FLAG_BAD_S], 1); bad_s[i] = 1; }
 }
 
 __global__ void __launch_bounds__(64)
@@ -178,7 +178,7 @@ __global__ void k_sum_final(const uint32_t *__restrict__ partial, uint32_t count
 template <int F64>
 __global__ void __launch_bounds__(128, PREP_MIN_BLOCKS)
 k_prep_R(const uint32_t *__restrict__ sigs, size_t cnt, ge_niels_packed *__restrict__ out_R, ge_niels_packed *__restrict__ out_B,
-         int *__restrict__ flags)
+         int *__restrict__ flags, uint8_t *__restrict__ bad_r)
 {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j > cnt || (j == cnt && !out_B)) return;
@@ -192,7 +192,7 @@ k_prep_R(const uint32_t *__restrict__ sigs, size_t cnt, ge_niels_packed *__restr
 #pragma unroll
         for (int k = 0; k < 8; k++) s[k] = sigs[16 * j + k];
         dst = out_R + j;
-        if (!ge_decompress_affine<F64>(x, y, s)) { atomicOr(&flags[FLAG_BAD_R], 1); fe_0(x); fe_1(y); }
+        if (!ge_decompress_affine<F64>(x, y, s)) { atomicOr(&flags[FLAG_BAD_R], 1); bad_r[j] = 1; fe_0(x); fe_1(y); }
     }
     ge_niels nl; ge_affine_to_niels(nl, x, y);
     ge_niels_packed p; ge_niels_pack(p, nl);
@@ -243,7 +243,8 @@ k_key_dedupe(const uint32_t *__restrict__ keys /* all n keys */, size_t i0, size
 template <int F64>
 __global__ void __launch_bounds__(128, PREP_MIN_BLOCKS)
 k_prep_A(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ uniq, const uint32_t *__restrict__ lo,
-         const uint32_t *__restrict__ hi, size_t i0, size_t cnt, ge_niels_packed *__restrict__ points_A, int *__restrict__ flags)
+         const uint32_t *__restrict__ hi, size_t i0, size_t cnt, ge_niels_packed *__restrict__ points_A, int *__restrict__ flags,
+         uint8_t *__restrict__ bad_key /* by slot */)
 {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t i, slot;
@@ -252,7 +253,7 @@ k_prep_A(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ uniq, c
 #pragma unroll
     for (int k = 0; k < 8; k++) s[k] = keys[8 * i + k];
     fe x, y;
-    if (!ge_decompress_affine<F64>(x, y, s)) { atomicOr(&flags[FLAG_BAD_A], 1); fe_0(x); fe_1(y); }
+    if (!ge_decompress_affine<F64>(x, y, s)) { atomicOr(&flags[FLAG_BAD_A], 1); bad_key[slot] = 1; fe_0(x); fe_1(y); }
     ge_niels nl; ge_affine_to_niels(nl, x, y);
     ge_niels_packed p; ge_niels_pack(p, nl);
     uint4 *o = reinterpret_cast<uint4 *>(points_A + slot);
@@ -305,11 +306,27 @@ __global__ void k_key_finalize(const unsigned long long *__restrict__ acc, size_
     for (int k = 0; k < 8; k++) out[8 * j + k] = r[k];
 }
 
+// per batch of `batch` signatures: bit 0 = some s not canonical, bit 1 = some R undecodable, bit 2 = some key undecodable
+__global__ void k_batch_status(const uint8_t *__restrict__ bad_s, const uint8_t *__restrict__ bad_r, const uint8_t *__restrict__ bad_key,
+                               const uint32_t *__restrict__ rep, const uint32_t *__restrict__ dense, int merged, size_t n, size_t batch,
+                               size_t nbatches, uint8_t *__restrict__ out)
+{
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nbatches) return;
+    uint32_t v = 0;
+    const size_t hi = min(n, (k + 1) * batch);
+    for (size_t i = k * batch; i < hi; i++) {
+        const size_t slot = merged ? dense[rep[i]] : i;
+        v |= (uint32_t)bad_s[i] | ((uint32_t)bad_r[i] << 1) | ((uint32_t)bad_key[slot] << 2);
+    }
+    out[k] = (uint8_t)v;
+}
+
 // ------------------------------------------------------------------------------------------
 // MSM inputs: scalars/points [0] = (-sum z s, B); [1 .. 1+K) = the K distinct keys (K = n without merging);
 // [1+n .. 1+2n) = (z_i, R_i).  counters: [0] running number of distinct keys, [1+p] its value after piece p, [15] = 0.
 struct VerifyBufs { uint32_t *hrams, *hs, *zsprod, *zs, *scalars; ge_niels_packed *points; int *flags;
-                    uint32_t *table, tmask, *rep, *uniq, *dense, *counters; };
+                    uint32_t *table, tmask, *rep, *uniq, *dense, *counters; uint8_t *bad_s, *bad_r, *bad_key; };
 
 static int verify_reserve(dalek_b200_ctx *ctx, size_t n, VerifyBufs &b)
 {
@@ -338,6 +355,9 @@ static int verify_reserve(dalek_b200_ctx *ctx, size_t n, VerifyBufs &b)
         CUDA_TRY(ctx, cudaMemsetAsync(b.table, 0xff, tsize * 4, ctx->stream));
         CUDA_TRY(ctx, cudaMemsetAsync(b.counters, 0, 64, ctx->stream));
     }
+    if ((rc = ws_reserve(ctx, ctx->sig_status, 3 * n1))) return rc;          // per-signature / per-key failure marks
+    b.bad_s = (uint8_t *)ctx->sig_status.p; b.bad_r = b.bad_s + n1; b.bad_key = b.bad_r + n1;
+    CUDA_TRY(ctx, cudaMemsetAsync(b.bad_s, 0, 3 * n1, ctx->stream));
     return 0;
 }
 
@@ -354,28 +374,28 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
     if (cnt) {
         // the hashing -> transcript chain has little parallelism in its second stage: enqueue it first
         k_hram<<<cdiv(cnt, 128), 128, 0, st>>>(d_msgs, d_offs + i0, d_sigs + 16 * i0, d_keys + 8 * i0, cnt, b.hrams + 16 * i0,
-                                               b.hs + 8 * i0, b.flags);
+                                               b.hs + 8 * i0, b.flags, b.bad_s + i0);
         size_t nchunks = (cnt + chunk - 1) / chunk;
         k_transcript<<<cdiv(nchunks, 64), 64, 0, st>>>(b.hrams + 16 * i0, d_sigs + 16 * i0, cnt, chunk, b.zs + 4 * i0);
         ctx->launches += 2;
     }
     ge_niels_packed *points_A = b.points + 1;
     if (ctx->opt_decompress_f64)
-        k_prep_R<1><<<cdiv(cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, cnt, b.points + 1 + n + i0, i0 == 0 ? b.points : nullptr, b.flags);
+        k_prep_R<1><<<cdiv(cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, cnt, b.points + 1 + n + i0, i0 == 0 ? b.points : nullptr, b.flags, b.bad_r + i0);
     else
-        k_prep_R<0><<<cdiv(cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, cnt, b.points + 1 + n + i0, i0 == 0 ? b.points : nullptr, b.flags);
+        k_prep_R<0><<<cdiv(cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, cnt, b.points + 1 + n + i0, i0 == 0 ? b.points : nullptr, b.flags, b.bad_r + i0);
     ctx->launches++;
     if (ctx->opt_dedupe_keys) {
         // keys first seen in this piece are uniq[counters[piece] .. counters[1 + piece])  (counters[15] = 0 for piece 0)
         const uint32_t *lo = piece ? b.counters + piece : b.counters + 15, *hi = b.counters + 1 + piece;
         if (cnt) k_key_dedupe<<<cdiv(cnt, 256), 256, 0, st2>>>(d_keys, i0, cnt, b.table, b.tmask, b.rep, b.uniq, b.dense, b.counters);
         CUDA_TRY(ctx, cudaMemcpyAsync(b.counters + 1 + piece, b.counters, 4, cudaMemcpyDeviceToDevice, st2));
-        if (cnt && ctx->opt_decompress_f64) k_prep_A<1><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, b.uniq, lo, hi, i0, cnt, points_A, b.flags);
-        else if (cnt) k_prep_A<0><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, b.uniq, lo, hi, i0, cnt, points_A, b.flags);
+        if (cnt && ctx->opt_decompress_f64) k_prep_A<1><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, b.uniq, lo, hi, i0, cnt, points_A, b.flags, b.bad_key);
+        else if (cnt) k_prep_A<0><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, b.uniq, lo, hi, i0, cnt, points_A, b.flags, b.bad_key);
         ctx->launches += cnt ? 2 : 0;
     } else if (cnt) {
-        if (ctx->opt_decompress_f64) k_prep_A<1><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, nullptr, nullptr, nullptr, i0, cnt, points_A, b.flags);
-        else k_prep_A<0><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, nullptr, nullptr, nullptr, i0, cnt, points_A, b.flags);
+        if (ctx->opt_decompress_f64) k_prep_A<1><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, nullptr, nullptr, nullptr, i0, cnt, points_A, b.flags, b.bad_key);
+        else k_prep_A<0><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, nullptr, nullptr, nullptr, i0, cnt, points_A, b.flags, b.bad_key);
         ctx->launches++;
     }
     if (cnt) {
@@ -389,52 +409,84 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
     return 0;
 }
 
-// -sum z_i s_i, the per-key scalars, the MSM (batch.rs:240-244) and the verdict
-static int verify_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, int pieces)
+// Joins the two front-end streams and returns the number of distinct keys (n without key merging).
+static int verify_join(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, int pieces, size_t *nkeys)
 {
     int rc;
     cudaStream_t st = ctx->stream, st2 = ctx->stream2;
-    const uint32_t nsum = 32768;
-    k_sum_partial<<<cdiv(nsum, 128), 128, 0, st>>>(b.zsprod, n, nsum, (uint32_t *)ctx->misc5.p);
-    k_sum_final<<<1, 256, 0, st>>>((const uint32_t *)ctx->misc5.p, nsum, b.scalars);
-    ctx->launches += 2;
     ctx->last_zs_n = n;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, st2));
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     if ((rc = pinned_reserve(ctx, sizeof(MsmResult) + 128))) return rc;
-    size_t nkeys = n;
+    *nkeys = n;
     if (ctx->opt_dedupe_keys && n) {
         // the number of distinct keys sizes the MSM: one small read-back in the middle of the call
         uint32_t *hk = (uint32_t *)((char *)ctx->h_pinned + sizeof(MsmResult) + 64);
         CUDA_TRY(ctx, cudaMemcpyAsync(hk, b.counters + pieces, 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        nkeys = *hk;
-        if (nkeys == 0 || nkeys > n) { ctx->last_error = "key table corrupted"; return -4; }
-        if (nkeys == n) {
+        *nkeys = *hk;
+        if (*nkeys == 0 || *nkeys > n) { ctx->last_error = "key table corrupted"; return -4; }
+    }
+    return 0;
+}
+
+// The equation of batch.rs:240-250 restricted to signatures [lo, hi):
+//   [-sum z_i s_i] B + sum z_i R_i + sum_keys [sum_{i of that key} z_i h_i] A_key  ==  identity ?
+static int verify_equation(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, size_t nkeys, size_t lo, size_t hi, bool *is_identity)
+{
+    int rc;
+    cudaStream_t st = ctx->stream;
+    const size_t cnt = hi - lo;
+    const uint32_t nsum = (uint32_t)std::min<size_t>(32768, std::max<size_t>(1, cnt));
+    k_sum_partial<<<cdiv(nsum, 128), 128, 0, st>>>(b.zsprod + 8 * lo, cnt, nsum, (uint32_t *)ctx->misc5.p);
+    k_sum_final<<<1, 256, 0, st>>>((const uint32_t *)ctx->misc5.p, nsum, b.scalars);
+    ctx->launches += 2;
+    const bool merged = ctx->opt_dedupe_keys && n;
+    if (merged) {
+        if (nkeys == n && cnt == n) {
             k_key_gather<<<cdiv(n, 256), 256, 0, st>>>(b.hs, b.uniq, n, b.scalars + 8);
             ctx->launches++;
         } else {
             if ((rc = ws_reserve(ctx, ctx->key_acc, nkeys * 64))) return rc;
             unsigned long long *acc = (unsigned long long *)ctx->key_acc.p;
             CUDA_TRY(ctx, cudaMemsetAsync(acc, 0, nkeys * 64, st));
-            k_key_accumulate<<<cdiv(n, 256), 256, 0, st>>>(b.hs, b.rep, b.dense, n, acc);
+            if (cnt) k_key_accumulate<<<cdiv(cnt, 256), 256, 0, st>>>(b.hs + 8 * lo, b.rep + lo, b.dense, cnt, acc);
             k_key_finalize<<<cdiv(nkeys, 128), 128, 0, st>>>(acc, nkeys, b.scalars + 8);
             ctx->launches += 2;
         }
     }
     // the z_i are 128-bit (batch.rs:224-229): their terms only populate the low windows
-    const int c = msm_choose_window_bits_mixed(ctx, n, 128, nkeys + 1);
+    const size_t nlong = merged ? nkeys + 1 : cnt + 1;
+    const int c = msm_choose_window_bits_mixed(ctx, cnt, 128, nlong);
     const int nwin = msm_window_count_for_bits(c);
     if ((rc = ws_reserve(ctx, ctx->misc0, (size_t)nwin * sizeof(ge_p3_raw)))) return rc;
     if ((rc = ws_reserve(ctx, ctx->result, sizeof(MsmResult)))) return rc;
-    if ((rc = msm_accumulate_chunk(ctx, b.scalars, b.points, PK_NIELS, nkeys + 1, c, true))) return rc;
-    if (n && (rc = msm_accumulate_chunk(ctx, b.scalars + 8 * (1 + n), b.points + 1 + n, PK_NIELS, n, c, false, (128 + c) / c))) return rc;
+    if (merged || cnt == n) {
+        if ((rc = msm_accumulate_chunk(ctx, b.scalars, b.points, PK_NIELS, nlong, c, true))) return rc;
+    } else {           // one term per signature, sub-range: the basepoint term, then the keys of the range
+        if ((rc = msm_accumulate_chunk(ctx, b.scalars, b.points, PK_NIELS, 1, c, true))) return rc;
+        if (cnt && (rc = msm_accumulate_chunk(ctx, b.scalars + 8 * (1 + lo), b.points + 1 + lo, PK_NIELS, cnt, c, false))) return rc;
+    }
+    if (cnt && (rc = msm_accumulate_chunk(ctx, b.scalars + 8 * (1 + n + lo), b.points + 1 + n + lo, PK_NIELS, cnt, c, false, (128 + c) / c))) return rc;
     if ((rc = msm_reduce_finish(ctx, c, (ge_p3_raw *)ctx->misc0.p, (MsmResult *)ctx->result.p))) return rc;
     MsmResult *h = (MsmResult *)ctx->h_pinned;
-    int *hflags = (int *)((char *)ctx->h_pinned + sizeof(MsmResult));
     CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->result.p, sizeof(MsmResult), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(hflags, b.flags, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    *is_identity = h->is_identity != 0;
+    return 0;
+}
+
+// the single verdict of verify_batch
+static int verify_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, int pieces)
+{
+    int rc;
+    size_t nkeys = 0;
+    bool ident = false;
+    if ((rc = verify_join(ctx, b, n, pieces, &nkeys))) return rc;
+    if ((rc = verify_equation(ctx, b, n, nkeys, 0, n, &ident))) return rc;
+    int *hflags = (int *)((char *)ctx->h_pinned + sizeof(MsmResult));
+    CUDA_TRY(ctx, cudaMemcpyAsync(hflags, b.flags, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
     // error precedence follows the reference: VerifyingKey::from_bytes happens before verify_batch
@@ -442,11 +494,53 @@ static int verify_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, int p
     if (hflags[FLAG_BAD_A]) return ED25519_ERR_POINT_DECOMPRESSION;
     if (hflags[FLAG_BAD_S]) return ED25519_ERR_SCALAR_FORMAT;
     if (hflags[FLAG_BAD_R]) return ED25519_ERR_VERIFY;
-    return h->is_identity ? DALEK_OK : ED25519_ERR_VERIFY;
+    return ident ? DALEK_OK : ED25519_ERR_VERIFY;
 }
 
+// Many independent batches of `batch` signatures in one call (the result of verify_batch on each): the
+// combined equation over all of them is tested first -- every batch has its own transcript, so the z_i of
+// different batches are independent and a failing batch leaves the total non-zero except with probability
+// ~2^-128 -- and only when it fails are halves re-tested down to single batches.
+static int verify_batches_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, int pieces, size_t batch, int32_t *verdicts)
+{
+    int rc;
+    size_t nkeys = 0;
+    const size_t nb = (n + batch - 1) / batch;
+    if ((rc = verify_join(ctx, b, n, pieces, &nkeys))) return rc;
+    if (nb == 0) return DALEK_OK;
+    if ((rc = ws_reserve(ctx, ctx->misc6, nb))) return rc;
+    k_batch_status<<<cdiv(nb, 128), 128, 0, ctx->stream>>>(b.bad_s, b.bad_r, b.bad_key, b.rep, b.dense, ctx->opt_dedupe_keys ? 1 : 0, n, batch,
+                                                             nb, (uint8_t *)ctx->misc6.p);
+    ctx->launches++;
+    std::vector<uint8_t> status(nb);
+    CUDA_TRY(ctx, cudaMemcpyAsync(status.data(), ctx->misc6.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<uint8_t> eq_ok(nb, 0);
+    std::vector<std::pair<size_t, size_t>> todo{{0, nb}};               // ranges of batches still to be tested
+    while (!todo.empty()) {
+        auto [k0, k1] = todo.back();
+        todo.pop_back();
+        bool ident = false;
+        if ((rc = verify_equation(ctx, b, n, nkeys, k0 * batch, std::min(n, k1 * batch), &ident))) return rc;
+        if (ident) { for (size_t k = k0; k < k1; k++) eq_ok[k] = 1; continue; }
+        if (k1 - k0 == 1) continue;
+        const size_t mid = k0 + (k1 - k0) / 2;
+        todo.push_back({mid, k1});
+        todo.push_back({k0, mid});
+    }
+    int any = 0;
+    for (size_t k = 0; k < nb; k++) {
+        int v = (status[k] & 4) ? ED25519_ERR_POINT_DECOMPRESSION : (status[k] & 1) ? ED25519_ERR_SCALAR_FORMAT
+                : ((status[k] & 2) || !eq_ok[k]) ? ED25519_ERR_VERIFY : DALEK_OK;
+        verdicts[k] = v;
+        any |= v;
+    }
+    return any ? ED25519_ERR_VERIFY : DALEK_OK;
+}
+
+// batch = 0: one verdict (verify_batch); batch > 0: independent batches of that many signatures, verdicts[k] each
 static int verify_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t *d_offs, const uint32_t *d_sigs,
-                      const uint32_t *d_keys, size_t n)
+                      const uint32_t *d_keys, size_t n, size_t batch, int32_t *verdicts)
 {
     int rc;
     VerifyBufs b;
@@ -454,8 +548,18 @@ static int verify_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t
     CUDA_TRY(ctx, cudaMemsetAsync(b.flags, 0, 64, ctx->stream));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     if ((rc = verify_front(ctx, b, d_msgs, d_offs, d_sigs, d_keys, n, 0, n, ctx->ev_fork))) return rc;
-    return verify_tail(ctx, b, n, 1);
+    return batch ? verify_batches_tail(ctx, b, n, 1, batch, verdicts) : verify_tail(ctx, b, n, 1);
 }
+
+// every batch gets exactly the reference's transcript: signatures per transcript = batch size for the call
+struct ChunkOverride {
+    dalek_b200_ctx *ctx; long saved;
+    ChunkOverride(dalek_b200_ctx *c, size_t batch) : ctx(c), saved(c->opt_verify_chunk) { if (batch) c->opt_verify_chunk = (long)batch; }
+    ~ChunkOverride() { ctx->opt_verify_chunk = saved; }
+};
+
+static int verify_host(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint64_t *msg_offsets, const uint8_t *sigs,
+                       const uint8_t *pubkeys, size_t n, size_t batch, int32_t *verdicts);
 
 extern "C" {
 
@@ -466,13 +570,39 @@ int ed25519_b200_verify_batch_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_f
     if (!ctx || (n && (!d_msg_offsets || !d_sigs || !d_pubkeys))) return DALEK_E_INVALID_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     return verify_dev(ctx, (const uint8_t *)d_msgs_flat, (const uint64_t *)d_msg_offsets, (const uint32_t *)d_sigs,
-                      (const uint32_t *)d_pubkeys, n);
+                      (const uint32_t *)d_pubkeys, n, 0, nullptr);
+}
+
+int ed25519_b200_verify_batches_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat, const void *d_msg_offsets,
+                                         const void *d_sigs, const void *d_pubkeys, size_t n, size_t batch_size, int32_t *verdicts)
+{
+    if (!ctx || !batch_size || batch_size > (1u << 20) || (n && (!d_msg_offsets || !d_sigs || !d_pubkeys || !verdicts))) return DALEK_E_INVALID_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ChunkOverride guard(ctx, batch_size);
+    return verify_dev(ctx, (const uint8_t *)d_msgs_flat, (const uint64_t *)d_msg_offsets, (const uint32_t *)d_sigs,
+                      (const uint32_t *)d_pubkeys, n, batch_size, verdicts);
+}
+
+int ed25519_b200_verify_batches_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint64_t *msg_offsets,
+                                     const uint8_t *sigs, const uint8_t *pubkeys, size_t n, size_t batch_size, int32_t *verdicts)
+{
+    if (!ctx || !batch_size || batch_size > (1u << 20) || (n && (!msg_offsets || !sigs || !pubkeys || !verdicts))) return DALEK_E_INVALID_ARG;
+    ChunkOverride guard(ctx, batch_size);
+    return verify_host(ctx, msgs_flat, msg_offsets, sigs, pubkeys, n, batch_size, verdicts);
 }
 
 int ed25519_b200_verify_batch_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint64_t *msg_offsets,
                                    const uint8_t *sigs, const uint8_t *pubkeys, size_t n)
 {
     if (!ctx || (n && (!msg_offsets || !sigs || !pubkeys))) return DALEK_E_INVALID_ARG;
+    return verify_host(ctx, msgs_flat, msg_offsets, sigs, pubkeys, n, 0, nullptr);
+}
+
+}  // extern "C"
+
+static int verify_host(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint64_t *msg_offsets, const uint8_t *sigs,
+                       const uint8_t *pubkeys, size_t n, size_t batch, int32_t *verdicts)
+{
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     int rc;
     size_t mbytes = n ? (size_t)msg_offsets[n] : 0;
@@ -507,8 +637,10 @@ int ed25519_b200_verify_batch_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_grp[k], sc));
         if ((rc = verify_front(ctx, b, d_msgs, d_offs, (const uint32_t *)d_sigs, (const uint32_t *)d_keys, n, i0, i1, ctx->ev_grp[k], k))) return rc;
     }
-    return verify_tail(ctx, b, n, K);
+    return batch ? verify_batches_tail(ctx, b, n, K, batch, verdicts) : verify_tail(ctx, b, n, K);
 }
+
+extern "C" {
 
 int ed25519_b200_verify_batch(dalek_b200_ctx *ctx, const uint8_t *const *msgs, const size_t *msg_lens,
                               const uint8_t *sigs, const uint8_t *pubkeys, size_t n)

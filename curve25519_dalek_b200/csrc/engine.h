@@ -26,7 +26,7 @@ struct dalek_b200_ctx {
     uint64_t launches = 0;
     // options
     long opt_window_bits = 0;
-    long opt_verify_chunk = 128;
+    long opt_verify_chunk = 64;
     long opt_host_chunks = 2;   // host-buffer MSM calls stream the pairs in this many chunks (copy/compute overlap)
     long opt_double_base_comb = 1; // double-base batch through the shared-memory fixed-base comb (0 = per-pair Straus)
     long opt_dedupe_keys = 1;   // verify_batch decompresses every distinct public key once
@@ -38,7 +38,7 @@ struct dalek_b200_ctx {
     int last_kernel_launches = 0;
     // device workspaces (grown on demand, reused across calls)
     DevBuf scalars, points_in, points, digits, counts, offsets, sorted, buckets, red_a, red_b, red_c,
-        red_d, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums, msg_offs, sum_desc, sum_part, key_table, key_acc;
+        red_d, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums, msg_offs, sum_desc, sum_part, key_table, key_acc, task_order, sig_status, misc6;
     int sum_desc_c = -1;
     bool base_table_ready = false;
     // pinned host staging

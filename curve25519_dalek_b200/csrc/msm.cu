@@ -9,7 +9,10 @@
 //                       generalised to c > 8), histogram of bucket sizes, rank inside the bucket
 //   k_scan_*            exclusive scan of the bucket sizes per window (multi-block)
 //   k_scatter           counting-sort scatter: point indices grouped by (window, bucket)
-//   k_task_*            buckets cut into tasks of <= 64 entries (skewed / adversarial inputs)
+//   k_task_count/fill   buckets cut into tasks of <= task_len entries (skewed / adversarial inputs)
+//   k_task_hist/scan/scatter
+//                       counting sort of the tasks by length: warps run equal trip counts and the
+//                       grid drains longest-first
 //   k_bucket_accumulate one thread per task: sum of its points with the complete unified mixed
 //                       addition (curve_models.rs:411-494), 7M (affine Niels) or 8M, on the
 //                       FP64-pipe field (fe64.cuh) with cp.async point prefetch
@@ -246,8 +249,7 @@ __global__ void k_scatter(const uint64_t *__restrict__ entries, const uint32_t *
 // Bucket accumulation as a list of tasks.  A task is at most task_len consecutive entries of one
 // bucket; a bucket with more entries (skewed inputs: the 128-bit z_i of verify_batch put n/256
 // points into each of 256 buckets of one window; adversarial inputs can put everything into one)
-// is cut into several tasks whose partial sums are added afterwards by k_heavy_fixup.  Inside a
-// CTA the 128 tasks are sorted by length so that the lanes of a warp run the same trip count.
+// is cut into several tasks whose partial sums are added afterwards by k_heavy_fixup.
 // task_len (msm_task_len) is twice the mean bucket size when the buckets alone give enough parallelism,
 // so that only genuinely skewed buckets are cut; with few buckets it is what yields >= 2^18 tasks.
 #define TASK_LEN_MIN 64u
@@ -301,6 +303,65 @@ __global__ void k_task_fill(const uint32_t *__restrict__ ntasks, const uint32_t 
     for (uint32_t j = 0; j < k; j++) tasks[base + j] = make_uint2(t, j);
 }
 
+// Tasks are processed in order of decreasing length (counting sort on the quantised length, TASK_BINS bins):
+// the lanes of a warp then run the same trip count, and the grid drains longest-first, so the kernel does not
+// end on a few long tasks.  order[q] = task index; hist | cursor | start are TASK_BINS words each.
+#define TASK_BINS 256u
+__device__ __forceinline__ uint32_t task_key(uint32_t len, uint32_t task_len)
+{
+    return (uint32_t)(((uint64_t)len * (TASK_BINS - 1) + task_len - 1) / task_len);     // 0 only for an empty task
+}
+__device__ __forceinline__ uint32_t task_length(const uint2 tk, const uint32_t *__restrict__ counts, uint32_t task_len)
+{
+    return min(task_len, counts[tk.x] - tk.y * task_len);
+}
+
+__global__ void __launch_bounds__(256)
+k_task_hist(const uint2 *__restrict__ tasks, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ total_ptr,
+            uint32_t task_len, uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t sh[TASK_BINS];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < *total_ptr) atomicAdd(&sh[task_key(task_length(tasks[p], counts, task_len), task_len)], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// start[k] = number of tasks with a larger key
+__global__ void __launch_bounds__(256) k_task_scan(const uint32_t *__restrict__ hist, uint32_t *__restrict__ start)
+{
+    __shared__ uint32_t sh[TASK_BINS];
+    const uint32_t k = TASK_BINS - 1 - threadIdx.x;              // thread 0 holds the largest key
+    sh[threadIdx.x] = hist[k];
+    __syncthreads();
+    for (uint32_t d = 1; d < TASK_BINS; d <<= 1) {
+        uint32_t v = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += v;
+        __syncthreads();
+    }
+    start[k] = sh[threadIdx.x] - hist[k];
+}
+
+__global__ void __launch_bounds__(256)
+k_task_scatter(const uint2 *__restrict__ tasks, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ total_ptr,
+               uint32_t task_len, const uint32_t *__restrict__ start, uint32_t *__restrict__ cursor, uint32_t *__restrict__ order)
+{
+    __shared__ uint32_t cnt[TASK_BINS], base[TASK_BINS];
+    cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = p < *total_ptr;
+    uint32_t key = 0, rank = 0;
+    if (live) { key = task_key(task_length(tasks[p], counts, task_len), task_len); rank = atomicAdd(&cnt[key], 1u); }
+    __syncthreads();
+    if (cnt[threadIdx.x]) base[threadIdx.x] = start[threadIdx.x] + atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]);
+    __syncthreads();
+    if (live) order[base[key] + rank] = p;
+}
+
 __device__ __forceinline__ void load_p3(ge_p3 &p, const ge_p3_raw *src)
 {
     const uint4 *s = reinterpret_cast<const uint4 *>(src);
@@ -314,40 +375,15 @@ template <int KIND, int F64>
 __global__ void __launch_bounds__(128, ACC_MIN_BLOCKS)
 k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict__ sorted,
                     const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets,
-                    const uint32_t *__restrict__ ntasks, const uint2 *__restrict__ tasks,
+                    const uint32_t *__restrict__ ntasks, const uint2 *__restrict__ tasks, const uint32_t *__restrict__ order,
                     const uint32_t *__restrict__ win_base, int w0, int w1, size_t n, uint32_t nbuckets, uint32_t task_len,
                     ge_p3_raw *__restrict__ buckets, ge_p3_raw *__restrict__ task_sums, int first)
 {
-    __shared__ uint32_t s_key[128];     // (len << 8) | local task index, sorted descending
     __shared__ uint4 s_pts[F64 ? 2 : 1][F64 ? 8 : 1][F64 ? 128 : 1];   // prefetch slots, [buffer][piece][thread]: conflict-free
     const uint32_t total_tasks = win_base[w1];            // this launch covers the tasks of windows [w0, w1)
-    const uint32_t p0 = win_base[w0] + blockIdx.x * 128u;
-    if (p0 >= total_tasks) return;
-    {
-        uint32_t p = p0 + threadIdx.x, len = 0;
-        if (p < total_tasks) {
-            uint2 tk = tasks[p];
-            uint32_t cnt = counts[tk.x], start = tk.y * task_len;
-            len = min(task_len, cnt - start) + 1;            // +1: empty tasks still sort above padding
-        }
-        s_key[threadIdx.x] = (len << 8) | threadIdx.x;
-        __syncthreads();
-        // bitonic sort of 128 keys, descending
-        for (uint32_t k = 2; k <= 128; k <<= 1) {
-            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                uint32_t i = threadIdx.x, ixj = i ^ j;
-                if (ixj > i) {
-                    uint32_t a = s_key[i], b = s_key[ixj];
-                    bool desc = (i & k) == 0;
-                    if (desc ? (a < b) : (a > b)) { s_key[i] = b; s_key[ixj] = a; }
-                }
-                __syncthreads();
-            }
-        }
-    }
-    const uint32_t key = s_key[threadIdx.x];
-    if ((key >> 8) == 0) return;                               // padding slot
-    const uint32_t p = p0 + (key & 0xff);
+    const uint32_t slot = blockIdx.x * 128u + threadIdx.x;
+    if (slot >= total_tasks) return;
+    const uint32_t p = order[slot];                        // tasks in order of decreasing length
     const uint2 tk = tasks[p];
     const uint32_t t = tk.x, w = t / nbuckets;
     const uint32_t cnt = counts[t], start = tk.y * task_len;
@@ -611,6 +647,7 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
     if ((rc = ws_reserve(ctx, ctx->task_off, total_buckets * 4 + (nwin + 1) * 4))) return rc;
     if ((rc = ws_reserve(ctx, ctx->tasks, max_tasks * 8))) return rc;
     if ((rc = ws_reserve(ctx, ctx->task_sums, max_tasks * sizeof(ge_p3_raw)))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->task_order, (3 * TASK_BINS + max_tasks) * 4))) return rc;   // hist | cursor | start | order
     if ((rc = ws_reserve(ctx, ctx->digits, std::max<size_t>(1, n) * nact * 8))) return rc;
     if ((rc = ws_reserve(ctx, ctx->sorted, std::max<size_t>(1, n) * nact * 4))) return rc;
     if ((rc = ws_reserve(ctx, ctx->buckets, total_buckets * sizeof(ge_p3_raw)))) return rc;
@@ -620,12 +657,15 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
     uint32_t *heavy = counts + total_buckets;
     uint32_t *part_sums = offsets + total_buckets;
     uint2 *tasks = (uint2 *)ctx->tasks.p;
+    uint32_t *t_hist = (uint32_t *)ctx->task_order.p, *t_cursor = t_hist + TASK_BINS, *t_start = t_cursor + TASK_BINS;
+    uint32_t *order = t_start + TASK_BINS;
     ge_p3_raw *task_sums = (ge_p3_raw *)ctx->task_sums.p;
     uint64_t *entries = (uint64_t *)ctx->digits.p;
     uint32_t *sorted = (uint32_t *)ctx->sorted.p;
     ge_p3_raw *buckets = (ge_p3_raw *)ctx->buckets.p;
 
     CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (total_buckets + 1) * 4, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(t_hist, 0, 2 * TASK_BINS * 4, st));
     if (n) {
         k_digits<<<cdiv(n, 256), 256, 0, st>>>((const uint4 *)d_scalars, n, c, nact, nb, counts, entries);
         ctx->launches++;
@@ -639,7 +679,10 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
     k_scan_apply<<<nwin * parts, 1024, 0, st>>>(ntasks, part_sums, nb, parts, task_off);
     k_task_bases<<<1, 32, 0, st>>>(ntasks, task_off, nb, nwin, win_base);
     k_task_fill<<<cdiv(total_buckets, 256), 256, 0, st>>>(ntasks, task_off, win_base, nb, (uint32_t)total_buckets, tasks);
-    ctx->launches += 9;
+    k_task_hist<<<cdiv(max_tasks, 256), 256, 0, st>>>(tasks, counts, win_base + nwin, task_len, t_hist);
+    k_task_scan<<<1, 256, 0, st>>>(t_hist, t_start);
+    k_task_scatter<<<cdiv(max_tasks, 256), 256, 0, st>>>(tasks, counts, win_base + nwin, task_len, t_start, t_cursor, order);
+    ctx->launches += 12;
     if (n) {
         const int wg = (int)std::max<size_t>(1, std::min<size_t>((size_t)nact, ((size_t)64 << 20) / (n * 4)));
         for (int w0 = 0; w0 < nact; w0 += wg) {
@@ -651,7 +694,7 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
     {
         const unsigned grid = cdiv(max_tasks, 128);
         const int f = first ? 1 : 0;
-#define LAUNCH_ACC(KIND_, F64_) k_bucket_accumulate<KIND_, F64_><<<grid, 128, 0, st>>>(d_points, sorted, counts, offsets, ntasks, tasks, win_base, 0, nwin, n, nb, task_len, buckets, task_sums, f)
+#define LAUNCH_ACC(KIND_, F64_) k_bucket_accumulate<KIND_, F64_><<<grid, 128, 0, st>>>(d_points, sorted, counts, offsets, ntasks, tasks, order, win_base, 0, nwin, n, nb, task_len, buckets, task_sums, f)
         if (point_kind == PK_NIELS) { if (ctx->opt_field_f64) LAUNCH_ACC(PK_NIELS, 1); else LAUNCH_ACC(PK_NIELS, 0); }
         else { if (ctx->opt_field_f64) LAUNCH_ACC(PK_PNIELS, 1); else LAUNCH_ACC(PK_PNIELS, 0); }
 #undef LAUNCH_ACC

@@ -45,6 +45,8 @@ def load_library():
     lib.ed25519_b200_verify_batch.argtypes = [vp, vp, vp, vp, vp, sz]
     lib.ed25519_b200_verify_batch_flat.argtypes = [vp, vp, vp, vp, vp, sz]
     lib.ed25519_b200_verify_batch_flat_dev.argtypes = [vp, vp, vp, vp, vp, sz, sz]
+    lib.ed25519_b200_verify_batches_flat.argtypes = [vp, vp, vp, vp, vp, sz, sz, vp]
+    lib.ed25519_b200_verify_batches_flat_dev.argtypes = [vp, vp, vp, vp, vp, sz, sz, vp]
     lib.ed25519_b200_last_zs.argtypes = [vp, vp, sz]
     lib.dalek_b200_edwards_mul_base_batch.argtypes = [vp, vp, sz, vp, vp]
     lib.ed25519_b200_sign_batch_flat.argtypes = [vp, vp, vp, vp, sz, vp, vp]
@@ -196,6 +198,15 @@ class Engine:
                                                                            _ptr(pubkeys), n, msgs_bytes))
         return self._check(self.lib.ed25519_b200_verify_batch_flat(self.h, _ptr(msgs_flat), _ptr(offsets), _ptr(sigs),
                                                                    _ptr(pubkeys), n))
+
+    def verify_batches_flat(self, msgs_flat, offsets, sigs, pubkeys, n, batch_size, device_ptrs=False):
+        """Independent batches of `batch_size` signatures in one call: (rc, verdicts) with verdicts[k] the result of
+        verify_batch on batch k (0 Ok, 1 Verify, 3 ScalarFormat, 4 PointDecompression); rc = 0 iff all are 0."""
+        nb = (n + batch_size - 1) // batch_size
+        verdicts = (C.c_int32 * max(nb, 1))()
+        fn = self.lib.ed25519_b200_verify_batches_flat_dev if device_ptrs else self.lib.ed25519_b200_verify_batches_flat
+        rc = self._check(fn(self.h, _ptr(msgs_flat), _ptr(offsets), _ptr(sigs), _ptr(pubkeys), n, batch_size, C.addressof(verdicts)))
+        return rc, list(verdicts)[:nb]
 
     def last_zs(self, n):
         out = (C.c_uint8 * (16 * max(n, 1)))()

@@ -58,7 +58,7 @@ int dalek_b200_init(int device, dalek_b200_ctx **out);
 void dalek_b200_destroy(dalek_b200_ctx *ctx);
 const char *dalek_b200_last_error(const dalek_b200_ctx *ctx);
 /* Tunables (none changes a result): "window_bits" (4..20, 0 = choose from n), "verify_chunk"
- * (signatures per transcript, default 128; see verify_batch below), "field_f64" (1 = bucket kernel
+ * (signatures per transcript, default 64; see verify_batch below), "field_f64" (1 = bucket kernel
  * on the FP64-pipe field, default; 0 = IMAD.WIDE field), "host_chunks" (1..4, host-buffer MSM calls
  * stream their input in this many chunks, default 2), "verify_pieces" (1..4, same for verify_batch,
  * default 4), "dedupe_keys" (1 = decompress every distinct public key once and give it one MSM term,
@@ -163,6 +163,20 @@ int ed25519_b200_verify_batch_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat
 int ed25519_b200_verify_batch_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat,
                                        const void *d_msg_offsets, const void *d_sigs,
                                        const void *d_pubkeys, size_t n, size_t msgs_bytes);
+/* Many independent batches in one call (2^14 batches of 256): signatures
+ * [k * batch_size, min(n, (k+1) * batch_size)) form batch k and verdicts[k] receives what
+ * ed25519_dalek::verify_batch (batch.rs:146-251) returns for that batch alone (0 / 1 / 3 / 4); each batch
+ * uses exactly the reference's transcript.  The combined equation over all batches is tested first
+ * (independent transcripts: a failing batch leaves it non-zero except with probability ~2^-128); only
+ * when it fails are halves re-tested down to single batches, so a clean call costs the same as one large
+ * verify_batch, and k failing batches add about k * log2(n / batch_size) partial re-tests.
+ * Returns 0 if every verdict is 0, 1 otherwise, negative on engine errors.  verdicts: ceil(n / batch_size) ints (host). */
+int ed25519_b200_verify_batches_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat,
+                                     const uint64_t *msg_offsets, const uint8_t *sigs,
+                                     const uint8_t *pubkeys, size_t n, size_t batch_size, int32_t *verdicts);
+int ed25519_b200_verify_batches_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat,
+                                         const void *d_msg_offsets, const void *d_sigs,
+                                         const void *d_pubkeys, size_t n, size_t batch_size, int32_t *verdicts);
 /* Debug/parity aid: the 16-byte z_i coefficients drawn in the last verify_batch call. */
 int ed25519_b200_last_zs(dalek_b200_ctx *ctx, uint8_t *zs_out, size_t n);
 

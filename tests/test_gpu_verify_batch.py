@@ -31,18 +31,21 @@ def make_batch(oracle, n, seed=0, msg_len=None):
     return msgs, sigs, pks
 
 
+CHUNK = 64          # the engine's default verify_chunk (signatures per Merlin transcript)
+
+
 def run(eng, msgs, sigs, pks):
     return eng.verify_batch_raw(msgs, b"".join(sigs), b"".join(pks))
 
 
-@pytest.mark.parametrize("n", [0, 1, 2, 7, 64, 95, 96, 128, 129, 300])
+@pytest.mark.parametrize("n", [0, 1, 2, 7, 63, 64, 65, 95, 96, 128, 129, 300])
 def test_verify_batch_valid_and_zs(eng, oracle, n):
     msgs, sigs, pks = make_batch(oracle, n, seed=n)
-    chunk = 128
+    chunk = CHUNK
     rc_o, zs_o = oracle.verify_batch(msgs, sigs, pks, chunk=chunk, want_zs=True)
     assert rc_o == OK
     assert run(eng, msgs, sigs, pks) == OK
-    assert eng.last_zs(n) == zs_o            # transcript parity (per chunk of 128)
+    assert eng.last_zs(n) == zs_o            # transcript parity (per chunk)
     if 0 < n <= chunk:                        # single chunk: exactly the reference's transcript
         rc_o, zs_ref = oracle.verify_batch(msgs, sigs, pks, want_zs=True)
         assert zs_ref == zs_o
@@ -57,7 +60,7 @@ def test_verify_batch_chunk_option(eng, oracle):
             rc, zs = oracle.verify_batch(msgs, sigs, pks, chunk=chunk, want_zs=True)
             assert eng.last_zs(50) == zs
         finally:
-            eng.set_option("verify_chunk", 128)
+            eng.set_option("verify_chunk", CHUNK)
 
 
 def test_verify_batch_negative_controls(eng, oracle):
@@ -165,10 +168,10 @@ def test_verify_batch_host_streaming_pieces(eng, oracle):
         else:
             assert zs == zs4                                # the coefficients do not depend on the piece count
     # z_i of the first transcript chunk agree with the oracle's
-    first = 128
+    first = CHUNK
     msgs = [flat[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(first)]
     rc, zo = oracle.verify_batch(msgs, [sg[64 * i:64 * i + 64].tobytes() for i in range(first)],
-                                 [pk[32 * i:32 * i + 32].tobytes() for i in range(first)], chunk=128, want_zs=True)
+                                 [pk[32 * i:32 * i + 32].tobytes() for i in range(first)], chunk=CHUNK, want_zs=True)
     assert rc == OK and zs4[:16 * first] == zo
 
 
@@ -211,11 +214,104 @@ def test_verify_batch_key_merging_edges(eng, oracle):
     # signature 77 must really be by key 3: rebuild both from one seed
     pks[3] = pks[77] = oracle.public_key(sk)
     sigs[3], sigs[77] = oracle.sign(msgs[3], sk), oracle.sign(msgs[77], sk)
-    assert run(eng, msgs, sigs, pks) == OK == oracle.verify_batch(msgs, sigs, pks, chunk=128)
+    assert run(eng, msgs, sigs, pks) == OK == oracle.verify_batch(msgs, sigs, pks, chunk=CHUNK)
     swapped = list(sigs); swapped[3], swapped[77] = sigs[77], sigs[3]
-    assert run(eng, msgs, swapped, pks) == VERIFY == oracle.verify_batch(msgs, swapped, pks, chunk=128)
+    assert run(eng, msgs, swapped, pks) == VERIFY == oracle.verify_batch(msgs, swapped, pks, chunk=CHUNK)
     one_key = [oracle.public_key(sk)] * 150
     one_sigs = [oracle.sign(m, sk) for m in msgs]
     assert run(eng, msgs, one_sigs, one_key) == OK
     bad = list(one_sigs); x = bytearray(bad[149]); x[2] ^= 0x10; bad[149] = bytes(x)      # R of the last signature
-    assert run(eng, msgs, bad, one_key) == VERIFY == oracle.verify_batch(msgs, bad, one_key, chunk=128)
+    assert run(eng, msgs, bad, one_key) == VERIFY == oracle.verify_batch(msgs, bad, one_key, chunk=CHUNK)
+
+
+def _flat(msgs):
+    import numpy as np
+    offs = np.zeros(len(msgs) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(m) for m in msgs])
+    return np.frombuffer(b"".join(msgs) + b"\0", dtype=np.uint8).copy(), offs
+
+
+@pytest.mark.parametrize("dedupe", [1, 0])
+def test_verify_batches_independent_verdicts(eng, oracle, dedupe):
+    """Many independent batches in one call: verdicts[k] must be what the oracle's
+    verify_batch returns for batch k alone, the z_i those of one reference transcript per batch, for clean input,
+    for every error kind, and for failures in first / middle / last (ragged) batches."""
+    bs, n = 16, 630                                            # 40 batches, the last one has 6 signatures
+    rnd = random.Random(1234)
+    seeds = [rnd.randbytes(32) for _ in range(9)]
+    msgs = [rnd.randbytes(rnd.randrange(0, 90)) for _ in range(n)]
+    pks = [oracle.public_key(seeds[i % 9]) for i in range(n)]
+    sigs = [oracle.sign(msgs[i], seeds[i % 9]) for i in range(n)]
+    nb = (n + bs - 1) // bs
+
+    def expect(m, s, k):
+        out = []
+        for b in range(nb):
+            lo, hi = b * bs, min(n, (b + 1) * bs)
+            out.append(oracle.verify_batch(m[lo:hi], s[lo:hi], k[lo:hi]))
+        return out
+
+    def got(m, s, k):
+        flat, offs = _flat(m)
+        return eng.verify_batches_flat(flat, offs, b"".join(s), b"".join(k), n, bs)
+
+    eng.set_option("dedupe_keys", dedupe)
+    try:
+        rc, v = got(msgs, sigs, pks)
+        assert rc == OK and v == [OK] * nb == expect(msgs, sigs, pks)
+        zs = eng.last_zs(n)
+        for b in (0, 17, nb - 1):                              # one reference transcript per batch
+            lo, hi = b * bs, min(n, (b + 1) * bs)
+            rc_o, z_o = oracle.verify_batch(msgs[lo:hi], sigs[lo:hi], pks[lo:hi], want_zs=True)
+            assert rc_o == OK and zs[16 * lo:16 * hi] == z_o
+        # failures of every kind, spread over the call
+        m, s, k = list(msgs), list(sigs), list(pks)
+        m[5] = m[5] + b"!"                                     # batch 0: Verify
+        x = bytearray(s[16 * 7 + 3]); x[63] |= 0xf0; s[16 * 7 + 3] = bytes(x)        # batch 7: s >= l -> ScalarFormat
+        k[16 * 11 + 9] = (2).to_bytes(32, "little")            # batch 11: undecodable key -> PointDecompression
+        s[16 * 20] = (2).to_bytes(32, "little") + s[16 * 20][32:]                  # batch 20: undecodable R -> Verify
+        x = bytearray(s[16 * 25 + 1]); x[63] |= 0xf0; s[16 * 25 + 1] = bytes(x)      # batch 25: bad s AND bad key -> PointDecompression
+        k[16 * 25 + 2] = (2).to_bytes(32, "little")
+        x = bytearray(s[n - 1]); x[40] ^= 1; s[n - 1] = bytes(x)                   # last (ragged) batch: Verify
+        want = expect(m, s, k)
+        assert want[0] == VERIFY and want[7] == SCALARFMT and want[11] == POINTDEC and want[20] == VERIFY and want[25] == POINTDEC
+        assert want[nb - 1] == VERIFY and sum(1 for w in want if w) == 6
+        rc, v = got(m, s, k)
+        assert rc == VERIFY and v == want
+        # a single bad signature in the middle: exactly one verdict changes
+        m2 = list(msgs); m2[16 * 19 + 15] = b"x" + m2[16 * 19 + 15]
+        rc, v = got(m2, sigs, pks)
+        assert rc == VERIFY and v == [VERIFY if b == 19 else OK for b in range(nb)]
+    finally:
+        eng.set_option("dedupe_keys", 1)
+
+
+def test_verify_batches_large_device(eng, oracle):
+    """2^15 signatures as 128 batches of 256 (the reference's largest published batch size) from device memory."""
+    import hashlib
+    import numpy as np
+    import torch
+    n, bs, nk = 1 << 15, 256, 37
+    seeds_k = np.stack([np.frombuffer(hashlib.sha512(b"b%d" % k).digest()[:32], dtype=np.uint8) for k in range(nk)])
+    seeds = np.ascontiguousarray(seeds_k[np.arange(n) % nk])
+    offs = np.arange(n + 1, dtype=np.uint64) * 59
+    flat = np.random.Generator(np.random.PCG64(6)).integers(0, 256, size=59 * n, dtype=np.uint8)
+    pks, sigs = eng.sign_batch_flat(seeds, flat, offs, n)
+    pk = np.frombuffer(pks, dtype=np.uint8).copy(); sg = np.frombuffer(sigs, dtype=np.uint8).copy()
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(x if x.dtype == np.uint8 else x.view(np.int64)).to(dev) for x in (flat, offs, sg, pk)]
+    rc, v = eng.verify_batches_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, bs, device_ptrs=True)
+    assert rc == OK and v == [OK] * (n // bs)
+    zs = eng.last_zs(n)
+    b = 77                                                     # one batch against the oracle's single transcript
+    lo, hi = b * bs, (b + 1) * bs
+    msgs = [flat[59 * i:59 * i + 59].tobytes() for i in range(lo, hi)]
+    rc_o, z_o = oracle.verify_batch(msgs, [sg[64 * i:64 * i + 64].tobytes() for i in range(lo, hi)],
+                                    [pk[32 * i:32 * i + 32].tobytes() for i in range(lo, hi)], want_zs=True)
+    assert rc_o == OK and zs[16 * lo:16 * hi] == z_o
+    d[0][59 * (bs * 100 + 3) + 1] ^= 4                         # corrupt one message of batch 100 and one of batch 0
+    d[0][7] ^= 1
+    rc, v = eng.verify_batches_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, bs, device_ptrs=True)
+    assert rc == VERIFY and v == [VERIFY if k in (0, 100) else OK for k in range(n // bs)]
+    # the option set for the call is restored afterwards
+    assert eng.verify_batch_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, device_ptrs=True) == VERIFY
