@@ -28,17 +28,16 @@ int dalek_b200_init(int device, dalek_b200_ctx **out)
     if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_grp[0], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_grp[1], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_grp[2], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_grp[3], cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return DALEK_E_CUDA;
     }
+    for (int i = 0; i < 8; i++)
+        if (cudaEventCreateWithFlags(&ctx->ev_grp[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return DALEK_E_CUDA; }
     *out = ctx;
     return DALEK_OK;
 }
@@ -49,6 +48,7 @@ void dalek_b200_destroy(dalek_b200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->stream2);
+    cudaStreamSynchronize(ctx->stream3);
     DevBuf *bufs[] = {&ctx->scalars, &ctx->points_in, &ctx->points, &ctx->digits, &ctx->counts, &ctx->offsets,
                       &ctx->sorted, &ctx->buckets, &ctx->red_a, &ctx->red_b, &ctx->red_c, &ctx->red_d,
                       &ctx->result, &ctx->flags, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->misc3,
@@ -57,8 +57,8 @@ void dalek_b200_destroy(dalek_b200_ctx *ctx)
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     cudaEventDestroy(ctx->ev_join2);
-    for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev_grp[i]);
-    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2); cudaStreamDestroy(ctx->stream_copy);
+    for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev_grp[i]);
+    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2); cudaStreamDestroy(ctx->stream_copy); cudaStreamDestroy(ctx->stream3);
     delete ctx;
 }
 
@@ -68,11 +68,11 @@ int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value)
 {
     if (!ctx || !name) return DALEK_E_INVALID_ARG;
     if (!strcmp(name, "window_bits")) { if (value != 0 && (value < 4 || value > 20)) return DALEK_E_INVALID_ARG; ctx->opt_window_bits = value; return 0; }
-    if (!strcmp(name, "host_chunks")) { if (value < 1 || value > 4) return DALEK_E_INVALID_ARG; ctx->opt_host_chunks = value; return 0; }
+    if (!strcmp(name, "host_chunks")) { if (value < 1 || value > 8) return DALEK_E_INVALID_ARG; ctx->opt_host_chunks = value; return 0; }
     if (!strcmp(name, "decompress_f64")) { ctx->opt_decompress_f64 = value ? 1 : 0; return 0; }
     if (!strcmp(name, "double_base_comb")) { ctx->opt_double_base_comb = value ? 1 : 0; return 0; }
     if (!strcmp(name, "dedupe_keys")) { ctx->opt_dedupe_keys = value ? 1 : 0; return 0; }
-    if (!strcmp(name, "verify_pieces")) { if (value < 1 || value > 4) return DALEK_E_INVALID_ARG; ctx->opt_verify_pieces = value; return 0; }
+    if (!strcmp(name, "verify_pieces")) { if (value < 1 || value > 8) return DALEK_E_INVALID_ARG; ctx->opt_verify_pieces = value; return 0; }
     if (!strcmp(name, "field_f64")) { ctx->opt_field_f64 = value ? 1 : 0; return 0; }
     if (!strcmp(name, "verify_chunk")) { if (value < 1 || value > (1 << 20)) return DALEK_E_INVALID_ARG; ctx->opt_verify_chunk = value; return 0; }
     return DALEK_E_INVALID_ARG;
@@ -115,7 +115,7 @@ static int run_msm(dalek_b200_ctx *ctx, const void *scalars, const void *points_
     } else {
         if ((rc = ws_reserve(ctx, ctx->scalars, std::max<size_t>(1, n) * 32))) return rc;
         if ((rc = ws_reserve(ctx, ctx->points_in, std::max<size_t>(1, n) * pin))) return rc;
-        int K = n >= (1u << 18) ? (int)std::min<long>(4, std::max<long>(1, ctx->opt_host_chunks)) : 1;
+        int K = n >= (1u << 18) ? (int)std::min<long>(8, std::max<long>(1, ctx->opt_host_chunks)) : 1;
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_copy, ctx->ev_fork, 0));
         // equal pieces; more than two pieces do not pay: every piece re-runs the per-bucket passes

@@ -361,13 +361,15 @@ static int verify_reserve(dalek_b200_ctx *ctx, size_t n, VerifyBufs &b)
     return 0;
 }
 
-// Front end for signatures [i0, i1) (i0 a multiple of verify_chunk): hashing, transcript, coefficients on
-// the main (high-priority) stream; decompression on the second stream.  Both wait for `ready` if given.
+// Front end for signatures [i0, i1) (i0 a multiple of verify_chunk): hashing, transcript, coefficients on a
+// high-priority stream (the main one for even pieces, stream3 for odd ones: a transcript kernel is a
+// latency-bound chain of Keccak permutations on few warps, so consecutive pieces should overlap);
+// decompression on the low-priority stream.  All wait for `ready` if given.
 static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t *d_msgs, const uint64_t *d_offs,
                         const uint32_t *d_sigs, const uint32_t *d_keys, size_t n, size_t i0, size_t i1, cudaEvent_t ready,
                         int piece = 0)
 {
-    cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+    cudaStream_t st = (piece & 1) ? ctx->stream3 : ctx->stream, st2 = ctx->stream2;
     const size_t cnt = i1 - i0;
     const uint32_t chunk = (uint32_t)ctx->opt_verify_chunk;
     if (ready) { CUDA_TRY(ctx, cudaStreamWaitEvent(st, ready, 0)); CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ready, 0)); }
@@ -417,6 +419,8 @@ static int verify_join(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, int p
     ctx->last_zs_n = n;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, st2));
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join2, ctx->stream3));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join2, 0));
     if ((rc = pinned_reserve(ctx, sizeof(MsmResult) + 128))) return rc;
     *nkeys = n;
     if (ctx->opt_dedupe_keys && n) {
@@ -618,10 +622,10 @@ static int verify_host(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint
     CUDA_TRY(ctx, cudaMemsetAsync(b.flags, 0, 64, st));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
     CUDA_TRY(ctx, cudaStreamWaitEvent(sc, ctx->ev_fork, 0));
-    // stream the batch in up to 4 pieces (boundaries on verify_chunk multiples): the copy of piece k+1
+    // stream the batch in up to 8 pieces (boundaries on verify_chunk multiples): the copy of piece k+1
     // overlaps hashing / decompression of piece k
     const size_t vc = (size_t)ctx->opt_verify_chunk;
-    int K = n >= (1u << 18) ? (int)std::min<long>(4, std::max<long>(1, ctx->opt_verify_pieces)) : 1;
+    int K = n >= (1u << 18) ? (int)std::min<long>(8, std::max<long>(1, ctx->opt_verify_pieces)) : 1;
     size_t prev = 0;
     for (int k = 0; k < K; k++) {
         size_t i1 = k == K - 1 ? n : std::min(n, ((n * (k + 1) / K) / vc) * vc);     // equal pieces: the front end outlasts the copies

@@ -20,14 +20,15 @@ struct dalek_b200_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;
     cudaStream_t stream_copy = nullptr;
+    cudaStream_t stream3 = nullptr;      // second hashing/transcript chain (odd verify pieces)
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
-    cudaEvent_t ev_grp[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_grp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // one per input piece
     std::string last_error;
     uint64_t launches = 0;
     // options
     long opt_window_bits = 0;
     long opt_verify_chunk = 64;
-    long opt_host_chunks = 2;   // host-buffer MSM calls stream the pairs in this many chunks (copy/compute overlap)
+    long opt_host_chunks = 4;   // host-buffer MSM calls stream the pairs in this many chunks (copy/compute overlap)
     long opt_double_base_comb = 1; // double-base batch through the shared-memory fixed-base comb (0 = per-pair Straus)
     long opt_dedupe_keys = 1;   // verify_batch decompresses every distinct public key once
     long opt_verify_pieces = 4; // host-buffer verify_batch calls stream the signatures in this many pieces

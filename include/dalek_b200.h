@@ -59,9 +59,9 @@ void dalek_b200_destroy(dalek_b200_ctx *ctx);
 const char *dalek_b200_last_error(const dalek_b200_ctx *ctx);
 /* Tunables (none changes a result): "window_bits" (4..20, 0 = choose from n), "verify_chunk"
  * (signatures per transcript, default 64; see verify_batch below), "field_f64" (1 = bucket kernel
- * on the FP64-pipe field, default; 0 = IMAD.WIDE field), "host_chunks" (1..4, host-buffer MSM calls
- * stream their input in this many chunks, default 2), "verify_pieces" (1..4, same for verify_batch,
- * default 4), "dedupe_keys" (1 = decompress every distinct public key once and give it one MSM term,
+ * on the FP64-pipe field, default; 0 = IMAD.WIDE field), "host_chunks" (1..8, host-buffer MSM calls
+ * stream their input in this many chunks, default 4), "verify_pieces" (1..8, same for verify_batch,
+ * default 4), "decompress_f64" (1 = square-root exponentiation of decompression on the FP64 field, default), "dedupe_keys" (1 = decompress every distinct public key once and give it one MSM term,
  * default), "double_base_comb" (1 = fixed-base comb for double-base batches of >= 4096 pairs, default).
  * Returns 0 or DALEK_E_INVALID_ARG. */
 int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value);

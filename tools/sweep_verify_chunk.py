@@ -20,10 +20,10 @@ def run(bufs, device):
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / 6 * 1e3
 
-for chunk in (32, 64, 128, 256):
+for chunk in (64,):
     eng.set_option("verify_chunk", chunk)
     print("verify_chunk=%d device %.2f ms  host(4 pieces) %.2f ms" % (chunk, run(d, True), run(h, False)), flush=True)
-eng.set_option("verify_chunk", 128)
-for pieces in (1, 2, 3, 4):
+eng.set_option("verify_chunk", 64)
+for pieces in (4, 6, 8):
     eng.set_option("verify_pieces", pieces)
     print("verify_pieces=%d host %.2f ms" % (pieces, run(h, False)), flush=True)
