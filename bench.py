@@ -300,7 +300,7 @@ def run_msm(args, rank, world, local):
                                   "algorithmic_field_muls_per_launch": field_muls},
             "clocks": clocks,
         }
-    return line, eng, (rank, world, local)
+    return line, eng, wl
 
 
 def eng_window_bits(n):
@@ -428,6 +428,32 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
                      "bucket_kernel_ms": kms, "note": "integer-multiply bound (decompression + MSM)"},
         "clocks": clocks,
     }
+
+
+def run_precomputed(eng, wl, steps=10):
+    """VartimePrecomputedMultiscalarMul with the 2^20 points of the MSM workload as static points,
+    resident on the GPU; a call sends the scalars only (32 B per term, pinned host memory) and must give the same
+    encoding as the plain MSM."""
+    import ctypes as C
+    pre = C.c_void_p()
+    rc = eng.lib.dalek_b200_precomp_new(eng.h, wl.h_points.data_ptr(), 1, wl.n, C.byref(pre))
+    assert rc == 0
+    out = (C.c_uint8 * 32)()
+
+    def step():
+        rc = eng.lib.dalek_b200_precomp_mixed_msm(eng.h, pre, wl.h_scalars.data_ptr(), wl.n, None, None, 1, 0, C.addressof(out), None)
+        assert rc == 0
+    for _ in range(3):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    same = bytes(out) == wl.step_device_single()
+    eng.lib.dalek_b200_precomp_destroy(pre)
+    return {"metric": "precomputed-static-points MSM points/sec, scalars from pinned host memory", "value": wl.n / dt, "unit": "points/s",
+            "ms_per_step": dt * 1e3, "static_points": wl.n, "h2d_bytes_per_step": 32 * wl.n, "d2h_bytes_per_step": 192,
+            "matches_plain_msm": bool(same)}
 
 
 def run_double_base(eng, n=1 << 20, steps=3):
@@ -574,8 +600,9 @@ def main():
     if args.workload == "verify":
         line = run_verify(args, rank, world, local)
     else:
-        line, eng, _ = run_msm(args, rank, world, local)
+        line, eng, wl = run_msm(args, rank, world, local)
         if not args.no_extras and world == 1:
+            line["msm_precomputed"] = run_precomputed(eng, wl)
             v = run_verify(args, rank, world, local, eng=eng, steps=min(args.steps, 5), warmup=3)
             line["verify_batch"] = {k: v[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "config", "gpu_launches", "roofline")}
             # the same batch size with every public key different (no key de-duplication possible)

@@ -6,10 +6,13 @@ touches the CPU checker used by the tests.  Names follow the reference:
   EdwardsPoint.vartime_multiscalar_mul / optional_multiscalar_mul / multiscalar_mul
       (curve25519-dalek/src/traits.rs:78-262, src/edwards.rs:966-1031)
   RistrettoPoint.multiscalar_mul / vartime_multiscalar_mul (src/ristretto.rs:964-994)
+  VartimeEdwardsPrecomputation / VartimeRistrettoPrecomputation (traits.rs:290-406, edwards.rs:1038-1076)
   verify_batch (ed25519-dalek/src/batch.rs:146-251) and its SignatureError values.
 """
 from .engine import (Engine, EngineError, EdwardsPoint, RistrettoPoint, SignatureError, verify_batch, default_engine,
-                     library_path, load_library, POINTS_COMPRESSED, POINTS_EXTENDED)
+                     library_path, load_library, POINTS_COMPRESSED, POINTS_EXTENDED, POINTS_RISTRETTO,
+                     VartimeEdwardsPrecomputation, VartimeRistrettoPrecomputation)
 
 __all__ = ["Engine", "EngineError", "EdwardsPoint", "RistrettoPoint", "SignatureError", "verify_batch", "default_engine",
-           "library_path", "load_library", "POINTS_COMPRESSED", "POINTS_EXTENDED"]
+           "library_path", "load_library", "POINTS_COMPRESSED", "POINTS_EXTENDED", "POINTS_RISTRETTO",
+           "VartimeEdwardsPrecomputation", "VartimeRistrettoPrecomputation"]

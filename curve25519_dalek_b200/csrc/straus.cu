@@ -411,6 +411,26 @@ __global__ void k_ristretto_encode_result(const MsmResult *__restrict__ res, uin
     for (int k = 0; k < 8; k++) out[k] = enc[k];
 }
 
+// CompressedRistretto (device, n x 32 B) -> packed projective Niels; *d_bad set if one does not decode
+int ristretto_prepare_points(dalek_b200_ctx *ctx, const void *d_in, size_t n, void *d_out, int *d_bad)
+{
+    if (!n) return 0;
+    if (ctx->opt_decompress_f64) k_prep_ristretto<1><<<cdiv(n, 128), 128, 0, ctx->stream>>>((const uint32_t *)d_in, (ge_pniels_packed *)d_out, n, d_bad);
+    else k_prep_ristretto<0><<<cdiv(n, 128), 128, 0, ctx->stream>>>((const uint32_t *)d_in, (ge_pniels_packed *)d_out, n, d_bad);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+// RistrettoPoint::compress of an MSM result (device): 8 words at d_enc
+int ristretto_encode_result(dalek_b200_ctx *ctx, const MsmResult *d_res, uint32_t *d_enc)
+{
+    k_ristretto_encode_result<<<1, 1, 0, ctx->stream>>>(d_res, d_enc);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
 extern "C" {
 
 int dalek_b200_edwards_ct_msm(dalek_b200_ctx *ctx, const uint8_t *scalars, const void *points, int point_fmt, size_t n,

@@ -3,6 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+POINTS_RISTRETTO = 2
 POINTS_COMPRESSED = 0
 POINTS_EXTENDED = 1
 
@@ -47,6 +48,12 @@ def load_library():
     lib.ed25519_b200_verify_batch_flat_dev.argtypes = [vp, vp, vp, vp, vp, sz, sz]
     lib.ed25519_b200_verify_batches_flat.argtypes = [vp, vp, vp, vp, vp, sz, sz, vp]
     lib.ed25519_b200_verify_batches_flat_dev.argtypes = [vp, vp, vp, vp, vp, sz, sz, vp]
+    lib.dalek_b200_precomp_new.argtypes = [vp, vp, C.c_int, sz, C.POINTER(vp)]
+    lib.dalek_b200_precomp_len.argtypes = [vp]
+    lib.dalek_b200_precomp_len.restype = sz
+    lib.dalek_b200_precomp_destroy.argtypes = [vp]
+    lib.dalek_b200_precomp_destroy.restype = None
+    lib.dalek_b200_precomp_mixed_msm.argtypes = [vp, vp, vp, sz, vp, vp, C.c_int, sz, vp, vp]
     lib.ed25519_b200_last_zs.argtypes = [vp, vp, sz]
     lib.dalek_b200_edwards_mul_base_batch.argtypes = [vp, vp, sz, vp, vp]
     lib.ed25519_b200_sign_batch_flat.argtypes = [vp, vp, vp, vp, sz, vp, vp]
@@ -272,6 +279,78 @@ class EdwardsPoint:
         eng = engine or default_engine()
         rc, comp, _ = eng.edwards_ct_msm(b"".join(scalars), b"".join(points), len(scalars))
         return comp
+
+
+class _Precomputation:
+    """VartimePrecomputedMultiscalarMul (traits.rs:290-406): static points converted once, resident on the GPU."""
+    _FMT = POINTS_COMPRESSED
+
+    def __init__(self, static_points, engine=None, fmt=None):
+        """`new` (traits.rs:297-300): static_points = iterable of 32-byte encodings (or, with fmt=POINTS_EXTENDED, a
+        buffer of n x 20 u64 limbs passed as (buffer, n))."""
+        self.eng = engine or default_engine()
+        fmt = self._FMT if fmt is None else fmt
+        if fmt == POINTS_EXTENDED:
+            buf, n = static_points
+        else:
+            pts = list(static_points)
+            buf, n = b"".join(pts), len(pts)
+        h = C.c_void_p()
+        rc = self.eng._check(self.eng.lib.dalek_b200_precomp_new(self.eng.h, _ptr(buf) if n else None, fmt, n, C.byref(h)))
+        if rc == 1:
+            raise ValueError("a static point does not decode")
+        self.h = h
+
+    def __len__(self):                                   # traits.rs:303
+        return int(self.eng.lib.dalek_b200_precomp_len(self.h))
+
+    def is_empty(self):                                  # traits.rs:306
+        return len(self) == 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.eng.lib.dalek_b200_precomp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def optional_mixed_multiscalar_mul(self, static_scalars, dynamic_scalars, dynamic_points, dynamic_fmt=None):
+        """traits.rs:402-413.  A dynamic point that is None or undecodable gives None."""
+        ss, ds, dp = list(static_scalars), list(dynamic_scalars), list(dynamic_points)
+        assert len(ss) <= len(self), "more static scalars than static points"
+        assert len(ds) == len(dp), "dynamic scalars and points must have the same length"
+        if any(p is None for p in dp):
+            return None
+        out = (C.c_uint8 * 32)()
+        rc = self.eng._check(self.eng.lib.dalek_b200_precomp_mixed_msm(
+            self.eng.h, self.h, _ptr(b"".join(ss)) if ss else None, len(ss), _ptr(b"".join(ds)) if ds else None,
+            _ptr(b"".join(dp)) if dp else None, self._FMT if dynamic_fmt is None else dynamic_fmt, len(ds), C.addressof(out), None))
+        return None if rc == 1 else bytes(out)
+
+    def vartime_mixed_multiscalar_mul(self, static_scalars, dynamic_scalars, dynamic_points):
+        """traits.rs:357-383: .expect() on the optional form."""
+        r = self.optional_mixed_multiscalar_mul(static_scalars, dynamic_scalars, dynamic_points)
+        if r is None:
+            raise ValueError("should return some point")
+        return r
+
+    def vartime_multiscalar_mul(self, static_scalars):
+        """traits.rs:324-338."""
+        return self.vartime_mixed_multiscalar_mul(static_scalars, [], [])
+
+
+class VartimeEdwardsPrecomputation(_Precomputation):
+    """curve25519-dalek/src/edwards.rs:1038-1076 (CompressedEdwardsY encodings in and out)."""
+    _FMT = POINTS_COMPRESSED
+
+
+class VartimeRistrettoPrecomputation(_Precomputation):
+    """curve25519-dalek/src/ristretto.rs:1004-1049 (CompressedRistretto encodings in and out)."""
+    _FMT = POINTS_RISTRETTO
 
 
 class RistrettoPoint:

@@ -50,6 +50,7 @@ typedef struct dalek_b200_ctx dalek_b200_ctx;
 
 #define DALEK_POINTS_COMPRESSED 0         /* n x 32 B CompressedEdwardsY */
 #define DALEK_POINTS_EXTENDED 1           /* n x 20 x u64 radix-2^51 limbs */
+#define DALEK_POINTS_RISTRETTO 2          /* n x 32 B CompressedRistretto (precomputation API only) */
 
 /* -------- context ---------------------------------------------------------------------- */
 /* Create an engine context on CUDA device `device`.  Fails (no CPU fallback) if the device
@@ -118,6 +119,30 @@ int dalek_b200_edwards_msm_partial_dev(dalek_b200_ctx *ctx, const void *d_scalar
  * (pippenger.rs:159). */
 int dalek_b200_edwards_msm_combine(dalek_b200_ctx *ctx, const uint64_t *windows, int ranks,
                                    size_t n_total, uint8_t out_compressed[32], uint64_t out_limbs[20]);
+
+/* -------- VartimePrecomputedMultiscalarMul ---------------------------------
+ * C/traits.rs:290-406; VartimeEdwardsPrecomputation C/edwards.rs:1038-1076, VartimeRistrettoPrecomputation
+ * C/ristretto.rs:1004-1049 (serial backend: precomputed_straus.rs:33-127).  The static points are decoded
+ * and converted once and stay resident in device memory; later calls send scalars only.
+ *
+ * new (traits.rs:297-300): static_points in format DALEK_POINTS_* (RISTRETTO makes a Ristretto
+ * precomputation: Ristretto encodings in and out).  DALEK_NONE if an encoded static point does not decode. */
+typedef struct dalek_b200_precomp dalek_b200_precomp;
+int dalek_b200_precomp_new(dalek_b200_ctx *ctx, const void *static_points, int point_fmt, size_t n,
+                           dalek_b200_precomp **out);
+size_t dalek_b200_precomp_len(const dalek_b200_precomp *pre);     /* traits.rs:303 */
+void dalek_b200_precomp_destroy(dalek_b200_precomp *pre);
+/* optional_mixed_multiscalar_mul (traits.rs:402-413):  Q = sum a_i A_i + sum b_j B_j  with B_j the static
+ * points.  n_static may be smaller than len() (unused points are ignored, traits.rs:314-316); larger is
+ * DALEK_E_INVALID_ARG (the reference asserts).  n_dynamic = 0 gives vartime_multiscalar_mul
+ * (traits.rs:324-338).  DALEK_NONE if a dynamic point does not decode.  dynamic_fmt: EXTENDED, or the
+ * encoding matching the precomputation (COMPRESSED for Edwards, RISTRETTO for Ristretto).
+ * out_compressed: CompressedEdwardsY, or CompressedRistretto for a Ristretto precomputation. */
+int dalek_b200_precomp_mixed_msm(dalek_b200_ctx *ctx, const dalek_b200_precomp *pre,
+                                 const uint8_t *static_scalars, size_t n_static,
+                                 const uint8_t *dynamic_scalars, const void *dynamic_points,
+                                 int dynamic_fmt, size_t n_dynamic, uint8_t out_compressed[32],
+                                 uint64_t out_limbs[20]);
 
 /* -------- RistrettoPoint ----------------------------------------------------------------- */
 /* n independent RistrettoPoint::multiscalar_mul([a_i, b_i], [G, H]) (constant-time Straus,
