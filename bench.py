@@ -456,6 +456,34 @@ def run_precomputed(eng, wl, steps=10):
             "matches_plain_msm": bool(same)}
 
 
+def run_codecs(eng, wl, steps=5):
+    """batch codecs on the 2^20 points of the MSM workload, pinned host buffers in and out."""
+    import torch
+    n = wl.n
+    enc = torch.empty(32 * n, dtype=torch.uint8).pin_memory()
+    enc2 = torch.empty(32 * n, dtype=torch.uint8).pin_memory()
+    limbs = torch.empty(20 * n, dtype=torch.int64).pin_memory()
+    ok = torch.empty(n, dtype=torch.uint8).pin_memory()
+    lib, h = eng.lib, eng.h
+
+    def timed(fn):
+        fn(); fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            rc = fn()
+        dt = (time.perf_counter() - t0) / steps
+        assert rc == 0
+        return {"value": n / dt, "unit": "points/s", "ms_per_step": dt * 1e3, "device_span_ms": eng.last_kernel_ms()[0]}
+    out = {"points": n}
+    out["compress_batch"] = timed(lambda: lib.dalek_b200_edwards_compress_batch(h, wl.h_points.data_ptr(), n, enc.data_ptr()))
+    out["decompress_batch"] = timed(lambda: lib.dalek_b200_edwards_decompress_batch(h, enc.data_ptr(), n, limbs.data_ptr(), ok.data_ptr()))
+    out["ristretto_double_and_compress_batch"] = timed(
+        lambda: lib.dalek_b200_ristretto_double_and_compress_batch(h, wl.h_points.data_ptr(), n, enc2.data_ptr()))
+    assert lib.dalek_b200_edwards_compress_batch(h, limbs.data_ptr(), n, enc2.data_ptr()) == 0
+    out["round_trip_ok"] = bool(torch.equal(enc, enc2)) and bool(ok.all())
+    return out
+
+
 def run_double_base(eng, n=1 << 20, steps=3):
     """BASELINE configs[4]: RistrettoPoint::multiscalar_mul([a_i, b_i], [G, H]) for 2^20 pairs (constant-time
     contract), host buffers in, compressed points out (64 B in + 32 B out per pair)."""
@@ -603,6 +631,7 @@ def main():
         line, eng, wl = run_msm(args, rank, world, local)
         if not args.no_extras and world == 1:
             line["msm_precomputed"] = run_precomputed(eng, wl)
+            line["codecs"] = run_codecs(eng, wl)
             v = run_verify(args, rank, world, local, eng=eng, steps=min(args.steps, 5), warmup=3)
             line["verify_batch"] = {k: v[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "config", "gpu_launches", "roofline")}
             # the same batch size with every public key different (no key de-duplication possible)

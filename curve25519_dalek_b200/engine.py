@@ -54,6 +54,10 @@ def load_library():
     lib.dalek_b200_precomp_destroy.argtypes = [vp]
     lib.dalek_b200_precomp_destroy.restype = None
     lib.dalek_b200_precomp_mixed_msm.argtypes = [vp, vp, vp, sz, vp, vp, C.c_int, sz, vp, vp]
+    lib.dalek_b200_edwards_decompress_batch.argtypes = [vp, vp, sz, vp, vp]
+    lib.dalek_b200_ristretto_decompress_batch.argtypes = [vp, vp, sz, vp, vp]
+    lib.dalek_b200_edwards_compress_batch.argtypes = [vp, vp, sz, vp]
+    lib.dalek_b200_ristretto_double_and_compress_batch.argtypes = [vp, vp, sz, vp]
     lib.ed25519_b200_last_zs.argtypes = [vp, vp, sz]
     lib.dalek_b200_edwards_mul_base_batch.argtypes = [vp, vp, sz, vp, vp]
     lib.ed25519_b200_sign_batch_flat.argtypes = [vp, vp, vp, vp, sz, vp, vp]
@@ -188,6 +192,26 @@ class Engine:
         out = (C.c_uint8 * 32)()
         rc = self._check(self.lib.dalek_b200_ristretto_vartime_msm(self.h, _ptr(scalars), _ptr(points), n, C.addressof(out)))
         return rc, bytes(out)
+
+    # ---- batch codecs ----
+    def decompress_batch(self, encodings, n, ristretto=False):
+        """CompressedEdwardsY / CompressedRistretto decompress for n x 32 B: (rc, limbs [n x 20 u64], ok bytes)."""
+        limbs = (C.c_uint64 * (20 * max(n, 1)))()
+        ok = (C.c_uint8 * max(n, 1))()
+        fn = self.lib.dalek_b200_ristretto_decompress_batch if ristretto else self.lib.dalek_b200_edwards_decompress_batch
+        rc = self._check(fn(self.h, _ptr(encodings), n, C.addressof(limbs), C.addressof(ok)))
+        return rc, limbs, bytes(ok)[:n]
+
+    def compress_batch(self, limbs, n):
+        """EdwardsPoint::compress_batch for n points given as 20 u64 limbs each -> n x 32 B."""
+        out = (C.c_uint8 * (32 * max(n, 1)))()
+        self._check(self.lib.dalek_b200_edwards_compress_batch(self.h, _ptr(limbs), n, C.addressof(out)))
+        return bytes(out)[:32 * n]
+
+    def ristretto_double_and_compress_batch(self, limbs, n):
+        out = (C.c_uint8 * (32 * max(n, 1)))()
+        self._check(self.lib.dalek_b200_ristretto_double_and_compress_batch(self.h, _ptr(limbs), n, C.addressof(out)))
+        return bytes(out)[:32 * n]
 
     # ---- ed25519 ----
     def verify_batch_raw(self, messages, sigs, pubkeys):
@@ -326,9 +350,10 @@ class _Precomputation:
         if any(p is None for p in dp):
             return None
         out = (C.c_uint8 * 32)()
+        sb, db, pb = b"".join(ss), b"".join(ds), b"".join(dp)      # kept alive across the call
         rc = self.eng._check(self.eng.lib.dalek_b200_precomp_mixed_msm(
-            self.eng.h, self.h, _ptr(b"".join(ss)) if ss else None, len(ss), _ptr(b"".join(ds)) if ds else None,
-            _ptr(b"".join(dp)) if dp else None, self._FMT if dynamic_fmt is None else dynamic_fmt, len(ds), C.addressof(out), None))
+            self.eng.h, self.h, _ptr(sb) if ss else None, len(ss), _ptr(db) if ds else None, _ptr(pb) if dp else None,
+            self._FMT if dynamic_fmt is None else dynamic_fmt, len(ds), C.addressof(out), None))
         return None if rc == 1 else bytes(out)
 
     def vartime_mixed_multiscalar_mul(self, static_scalars, dynamic_scalars, dynamic_points):

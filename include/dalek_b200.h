@@ -144,6 +144,24 @@ int dalek_b200_precomp_mixed_msm(dalek_b200_ctx *ctx, const dalek_b200_precomp *
                                  int dynamic_fmt, size_t n_dynamic, uint8_t out_compressed[32],
                                  uint64_t out_limbs[20]);
 
+/* -------- batch wire-format codecs -----------------------------------------
+ * Points are the reference's in-memory EdwardsPoint / RistrettoPoint: 20 u64 limbs X | Y | Z | T, radix 2^51.
+ * Host buffers; the batch is streamed in pieces so that the copies overlap the arithmetic.
+ *
+ * CompressedEdwardsY::decompress (C/edwards.rs:211-257) for n encodings: ok[i] = 1 and out_limbs[20 i ..] =
+ * the point (Z = 1), or ok[i] = 0 (None; the slot holds the identity).  Returns DALEK_NONE if any ok[i] = 0. */
+int dalek_b200_edwards_decompress_batch(dalek_b200_ctx *ctx, const uint8_t *in, size_t n,
+                                        uint64_t *out_limbs, uint8_t *ok);
+/* EdwardsPoint::compress_batch (C/edwards.rs:619-647): n points -> n x 32 B, one shared inversion per 8
+ * points (FieldElement::invert_batch, C/field.rs:239-274). */
+int dalek_b200_edwards_compress_batch(dalek_b200_ctx *ctx, const uint64_t *limbs, size_t n, uint8_t *out);
+/* CompressedRistretto::decompress (C/ristretto.rs:266-345), same conventions as the Edwards form. */
+int dalek_b200_ristretto_decompress_batch(dalek_b200_ctx *ctx, const uint8_t *in, size_t n,
+                                          uint64_t *out_limbs, uint8_t *ok);
+/* RistrettoPoint::double_and_compress_batch (C/ristretto.rs:564-646): out[i] = compress(2 P_i). */
+int dalek_b200_ristretto_double_and_compress_batch(dalek_b200_ctx *ctx, const uint64_t *limbs, size_t n,
+                                                   uint8_t *out);
+
 /* -------- RistrettoPoint ----------------------------------------------------------------- */
 /* n independent RistrettoPoint::multiscalar_mul([a_i, b_i], [G, H]) (constant-time Straus,
  * C/ristretto.rs:964-977 -> C/edwards.rs:970-995 -> straus.rs:103-144), each result compressed

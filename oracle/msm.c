@@ -1,12 +1,15 @@
 /*
  * msm.c -- Pippenger and Straus multiscalar multiplication, with the
  * EdwardsPoint trait dispatch.  TEST INFRASTRUCTURE (oracle).
- * Restates C/backend/serial/scalar_mul/{pippenger,straus,vartime_double_base}.rs
- * and C/edwards.rs:966-1031.
+ * Restates C/backend/serial/scalar_mul/{pippenger,straus,vartime_double_base,precomputed_straus}.rs,
+ * C/edwards.rs:966-1031 and EdwardsPoint::compress_batch (C/edwards.rs:619-647).
  */
 #include "oracle.h"
+#include "constants.h"
 #include <stdlib.h>
 #include <string.h>
+
+static void fe_const(fe51 *o, const uint64_t k[5]) { memcpy(o->v, k, sizeof o->v); }
 
 /* scalar_mul/pippenger.rs:67-160 */
 int msm_pippenger(ge_p3 *o, const uint8_t *scalars, const ge_p3 *points,
@@ -165,4 +168,89 @@ int oracle_msm_limbs(uint64_t out_limbs[20], const uint8_t *scalars, const ge_p3
     if (!edwards_optional_multiscalar_mul(&r, scalars, points, NULL, n)) return 0;
     ge_p3_to_limbs(out_limbs, &r);
     return 1;
+}
+
+/* ---- VartimePrecomputedMultiscalarMul, serial backend ------------------------------------------------- */
+/* C/edwards.rs:551-561 */
+static void ge_p3_to_aniels(ge_aniels *o, const ge_p3 *p)
+{
+    fe51 recip, x, y, d2;
+    fe_const(&d2, K_EDWARDS_D2);
+    fe_invert(&recip, &p->Z);
+    fe_mul(&x, &p->X, &recip);
+    fe_mul(&y, &p->Y, &recip);
+    fe_add(&o->y_plus_x, &y, &x);
+    fe_sub(&o->y_minus_x, &y, &x);
+    fe_mul(&o->xy2d, &x, &y); fe_mul(&o->xy2d, &o->xy2d, &d2);
+}
+
+/* C/window.rs:266-276: [A, 3A, 5A, ..., 127A] as affine Niels points */
+typedef struct { ge_aniels t[64]; } ge_naf_table8;
+static void ge_naf_table8_from(ge_naf_table8 *t, const ge_p3 *a)
+{
+    ge_p3 a2;
+    ge_p3_to_aniels(&t->t[0], a);
+    ge_p3_double(&a2, a);
+    for (int i = 0; i < 63; i++) {
+        ge_p1p1 r; ge_p3 e;
+        ge_add_aniels(&r, &a2, &t->t[i]); ge_p1p1_to_p3(&e, &r); ge_p3_to_aniels(&t->t[i + 1], &e);
+    }
+}
+
+/* scalar_mul/precomputed_straus.rs:57-126 (the tables of :37-46 are rebuilt per call: the oracle keeps no state).
+ * n_static_points >= n_static (unused points are ignored, :88); a missing dynamic point gives None (:78-81). */
+int msm_precomputed_straus(ge_p3 *o, const uint8_t *static_scalars, size_t n_static, const ge_p3 *static_points,
+                           size_t n_static_points, const uint8_t *dynamic_scalars, const ge_p3 *dynamic_points,
+                           const uint8_t *present, size_t n_dynamic)
+{
+    if (n_static > n_static_points) return -1;                    /* :88 assert */
+    for (size_t i = 0; i < n_dynamic; i++) if (present && !present[i]) return 0;
+    int8_t *snaf = (int8_t *)malloc(256 * (n_static ? n_static : 1));
+    int8_t *dnaf = (int8_t *)malloc(256 * (n_dynamic ? n_dynamic : 1));
+    ge_naf_table8 *stab = (ge_naf_table8 *)malloc(sizeof(ge_naf_table8) * (n_static ? n_static : 1));
+    ge_naf_table5 *dtab = (ge_naf_table5 *)malloc(sizeof(ge_naf_table5) * (n_dynamic ? n_dynamic : 1));
+    for (size_t i = 0; i < n_static; i++) {
+        scalar_non_adjacent_form(snaf + 256 * i, static_scalars + 32 * i, 8);    /* :70-73 */
+        ge_naf_table8_from(&stab[i], &static_points[i]);
+    }
+    for (size_t i = 0; i < n_dynamic; i++) {
+        scalar_non_adjacent_form(dnaf + 256 * i, dynamic_scalars + 32 * i, 5);   /* :74-77 */
+        ge_naf_table5_from(&dtab[i], &dynamic_points[i]);
+    }
+    ge_p2 s; ge_p2_identity(&s);                                  /* :94 */
+    for (int j = 255; j >= 0; j--) {                              /* :95-123 */
+        ge_p1p1 r; ge_p3 e;
+        ge_p2_double(&r, &s);
+        for (size_t i = 0; i < n_dynamic; i++) {
+            int8_t d = dnaf[256 * i + j];
+            if (d > 0) { ge_p1p1_to_p3(&e, &r); ge_add_pniels(&r, &e, &dtab[i].t[d / 2]); }
+            else if (d < 0) { ge_p1p1_to_p3(&e, &r); ge_sub_pniels(&r, &e, &dtab[i].t[(-d) / 2]); }
+        }
+        for (size_t i = 0; i < n_static; i++) {
+            int8_t d = snaf[256 * i + j];
+            if (d > 0) { ge_p1p1_to_p3(&e, &r); ge_add_aniels(&r, &e, &stab[i].t[d / 2]); }
+            else if (d < 0) { ge_p1p1_to_p3(&e, &r); ge_sub_aniels(&r, &e, &stab[i].t[(-d) / 2]); }
+        }
+        ge_p1p1_to_p2(&s, &r);
+    }
+    ge_p2_to_p3(o, &s);                                           /* :125 */
+    free(snaf); free(dnaf); free(stab); free(dtab);
+    return 1;
+}
+
+/* ---- batch codecs ---------------------------------------------------------------------------------------- */
+/* EdwardsPoint::compress_batch_alloc, C/edwards.rs:633-647 */
+void ge_compress_batch(uint8_t *out, const ge_p3 *points, size_t n)
+{
+    fe51 *zs = (fe51 *)malloc(sizeof(fe51) * (n ? n : 1));
+    for (size_t i = 0; i < n; i++) zs[i] = points[i].Z;
+    fe_invert_batch(zs, n);
+    for (size_t i = 0; i < n; i++) {
+        fe51 x, y;
+        fe_mul(&x, &points[i].X, &zs[i]);
+        fe_mul(&y, &points[i].Y, &zs[i]);
+        fe_to_bytes(out + 32 * i, &y);                            /* edwards/affine.rs:71-75 */
+        out[32 * i + 31] ^= (uint8_t)(fe_is_negative(&x) << 7);
+    }
+    free(zs);
 }

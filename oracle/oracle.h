@@ -137,6 +137,12 @@ void edwards_vartime_double_scalar_mul_basepoint(ge_p3 *o, const uint8_t a[32], 
                                                  const uint8_t b[32]);
 
 /* helpers for tests / bench input synthesis (not reference functions) */
+/* scalar_mul/precomputed_straus.rs:57-126; 1 = Some, 0 = None, -1 = more static scalars than points */
+int  msm_precomputed_straus(ge_p3 *o, const uint8_t *static_scalars, size_t n_static, const ge_p3 *static_points,
+                            size_t n_static_points, const uint8_t *dynamic_scalars, const ge_p3 *dynamic_points,
+                            const uint8_t *present, size_t n_dynamic);
+void ge_compress_batch(uint8_t *out, const ge_p3 *points, size_t n);            /* C/edwards.rs:633-647 */
+void ristretto_double_and_compress_batch(uint8_t *out, const ge_p3 *points, size_t n);  /* C/ristretto.rs:564-646 */
 void oracle_points_progression(ge_p3 *out, size_t n, const uint8_t t0[32], const uint8_t q[32]);
 int  oracle_msm_compressed(uint8_t out[32], const uint8_t *scalars, const ge_p3 *points, size_t n);
 int  oracle_msm_limbs(uint64_t out_limbs[20], const uint8_t *scalars, const ge_p3 *points, size_t n);

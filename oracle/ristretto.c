@@ -1,10 +1,11 @@
 /*
  * ristretto.c -- Ristretto255 encode/decode/equality and the double-base batch.
  * TEST INFRASTRUCTURE (oracle).  Restates C/ristretto.rs:266-345, :500-533,
- * :815-830, :964-977.
+ * :564-646, :815-830, :964-977.
  */
 #include "oracle.h"
 #include "constants.h"
+#include <stdlib.h>
 #include <string.h>
 
 static void fe_const(fe51 *o, const uint64_t k[5]) { memcpy(o->v, k, sizeof o->v); }
@@ -94,4 +95,52 @@ int ristretto_double_base_batch(uint8_t *out, const uint8_t *a, const uint8_t *b
         ristretto_compress(out + 32 * i, &r);
     }
     return 0;
+}
+
+/* RistrettoPoint::double_and_compress_batch, C/ristretto.rs:564-646: out[i] = compress(2 P_i) with one
+ * simultaneous inversion (C/field.rs:239-273) and no square roots */
+void ristretto_double_and_compress_batch(uint8_t *out, const ge_p3 *points, size_t n)
+{
+    typedef struct { fe51 e, f, g, h, eg, fh; } state;
+    state *st = (state *)malloc(sizeof(state) * (n ? n : 1));
+    fe51 *invs = (fe51 *)malloc(sizeof(fe51) * (n ? n : 1));
+    fe51 d, sqrt_m1, invsqrt_a_minus_d;
+    fe_const(&d, K_EDWARDS_D); fe_const(&sqrt_m1, K_SQRT_M1); fe_const(&invsqrt_a_minus_d, K_INVSQRT_A_MINUS_D);
+    for (size_t i = 0; i < n; i++) {                              /* :584-601 */
+        const ge_p3 *P = &points[i];
+        fe51 XX, YY, ZZ, dTT, t;
+        fe_square(&XX, &P->X); fe_square(&YY, &P->Y); fe_square(&ZZ, &P->Z);
+        fe_square(&t, &P->T); fe_mul(&dTT, &t, &d);
+        fe_add(&t, &P->Y, &P->Y); fe_mul(&st[i].e, &P->X, &t);
+        fe_add(&st[i].f, &ZZ, &dTT);
+        fe_add(&st[i].g, &YY, &XX);
+        fe_sub(&st[i].h, &ZZ, &dTT);
+        fe_mul(&st[i].eg, &st[i].e, &st[i].g);
+        fe_mul(&st[i].fh, &st[i].f, &st[i].h);
+        fe_mul(&invs[i], &st[i].eg, &st[i].fh);                   /* :607 */
+    }
+    fe_invert_batch(invs, n);                                     /* :609 */
+    for (size_t i = 0; i < n; i++) {                              /* :611-644 */
+        fe51 Zinv, Tinv, magic = invsqrt_a_minus_d, t, e = st[i].e, g = st[i].g, h = st[i].h, minus_e, f_times_sqrta, s;
+        fe_mul(&Zinv, &st[i].eg, &invs[i]);
+        fe_mul(&Tinv, &st[i].fh, &invs[i]);
+        fe_mul(&t, &st[i].eg, &Zinv);
+        int negcheck1 = fe_is_negative(&t);
+        fe_neg(&minus_e, &e);
+        fe_mul(&f_times_sqrta, &st[i].f, &sqrt_m1);
+        fe_cond_assign(&e, &st[i].g, negcheck1);
+        fe_cond_assign(&g, &minus_e, negcheck1);
+        fe_cond_assign(&h, &f_times_sqrta, negcheck1);
+        fe_cond_assign(&magic, &sqrt_m1, negcheck1);
+        fe_mul(&t, &h, &e); fe_mul(&t, &t, &Zinv);
+        int negcheck2 = fe_is_negative(&t);
+        fe_cond_negate(&g, negcheck2);
+        fe51 hg, gt;
+        fe_sub(&hg, &h, &g);
+        fe_mul(&gt, &g, &Tinv); fe_mul(&gt, &magic, &gt);
+        fe_mul(&s, &hg, &gt);
+        fe_cond_negate(&s, fe_is_negative(&s));
+        fe_to_bytes(out + 32 * i, &s);
+    }
+    free(st); free(invs);
 }

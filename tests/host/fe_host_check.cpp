@@ -100,6 +100,11 @@ void h_fe64_pow_p58(uint8_t *o, const uint8_t *a)
     fe x, z; load(x, a);
     fe_pow_p58_f64(z, x); store(o, z);
 }
+void h_fe64_invert(uint8_t *o, const uint8_t *a)
+{
+    fe x, z; load(x, a);
+    fe_invert_f64(z, x); store(o, z);
+}
 void h_fe64_sq(uint8_t *o, const uint8_t *a, const uint8_t *b)
 {
     fe x, y, z; load(x, a); load(y, b);

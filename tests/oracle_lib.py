@@ -144,6 +144,33 @@ class Oracle:
         ok = fn(C.byref(o), buf(b"".join(scalars)), arr, pres, C.c_size_t(len(points)))
         return o if ok else None
 
+    def precomputed_straus(self, static_scalars, static_points, dynamic_scalars, dynamic_points):
+        """VartimePrecomputedStraus::optional_mixed_multiscalar_mul (precomputed_straus.rs:57-126); dynamic points may
+        hold None.  Returns the point, None, or raises if there are more static scalars than static points."""
+        sarr, _ = self._pts(static_points)
+        darr, pres = self._pts(dynamic_points)
+        o = P3()
+        rc = self.lib.msm_precomputed_straus(C.byref(o), buf(b"".join(static_scalars)), C.c_size_t(len(static_scalars)), sarr,
+                                             C.c_size_t(len(static_points)), buf(b"".join(dynamic_scalars)), darr, pres,
+                                             C.c_size_t(len(dynamic_points)))
+        if rc < 0:
+            raise ValueError("more static scalars than static points")
+        return o if rc else None
+
+    def compress_batch(self, points):
+        """EdwardsPoint::compress_batch (C/edwards.rs:619-647)."""
+        arr, _ = self._pts(points)
+        out = (C.c_uint8 * (32 * max(len(points), 1)))()
+        self.lib.ge_compress_batch(out, arr, C.c_size_t(len(points)))
+        return bytes(out)[:32 * len(points)]
+
+    def ristretto_double_and_compress_batch(self, points):
+        """RistrettoPoint::double_and_compress_batch (C/ristretto.rs:564-646)."""
+        arr, _ = self._pts(points)
+        out = (C.c_uint8 * (32 * max(len(points), 1)))()
+        self.lib.ristretto_double_and_compress_batch(out, arr, C.c_size_t(len(points)))
+        return bytes(out)[:32 * len(points)]
+
     def msm_ct(self, scalars, points):
         arr, _ = self._pts(points)
         o = P3()

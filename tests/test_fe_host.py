@@ -155,6 +155,7 @@ def test_fe64_model(host, oracle):
         assert call(host.h_fe64_sq, b32(x), b32(y)) == pow(pow(x, 4, p) * y, 2, p)
         if i < 60:
             assert call(host.h_fe64_pow_p58, b32(x)) == pow(x, (p - 5) // 8, p)
+            assert call(host.h_fe64_invert, b32(x)) == pow(x, p - 2, p)
     B = oracle.basepoint()
     ident = oracle.compress(oracle.identity())
     for trial in range(6):

@@ -46,6 +46,8 @@ def test_edwards_precomputed_matches_plain_msm(eng, oracle, ns, nd):
     want = oracle.compress(oracle.msm("optional", ss + ds, static_pts + dyn_pts)) if ns + nd else oracle.compress(oracle.identity())
     got = pre.vartime_mixed_multiscalar_mul(ss, ds, [oracle.compress(p) for p in dyn_pts])
     assert got == want
+    if ns + nd <= 200:                                          # the reference's own algorithm (precomputed_straus.rs:57-126)
+        assert oracle.compress(oracle.precomputed_straus(ss, static_pts, ds, dyn_pts)) == want
     # the object is reusable: a second call with other scalars, static part only
     ss2 = [b32(rnd.randrange(pyref.L)) for _ in range(ns)]
     want2 = oracle.compress(oracle.msm("optional", ss2, static_pts)) if ns else oracle.compress(oracle.identity())

@@ -310,3 +310,39 @@ def test_keccak_f1600_vs_hashlib_sha3(oracle):
     for n in [0, 1, 135, 136, 137, 500]:
         m = rnd.randbytes(n)
         assert sha3_256(m) == hashlib.sha3_256(m).digest()
+
+
+def test_precomputed_straus_and_batch_codecs(oracle, kat):
+    """The oracle's restatements of the SURVEY 8f rows against properties the reference tests:
+    precomputed == non-precomputed MSM (C/edwards.rs:2343-2417), compress_batch == compress of each point
+    (C/edwards.rs:1885-1901), double_and_compress_batch == compress(2P) (C/ristretto.rs:1683-1698)."""
+    rnd = random.Random(2026)
+    b32 = lambda x: x.to_bytes(32, "little")
+    B = oracle.basepoint()
+    sp = [oracle.scalarmul(b32(rnd.randrange(pyref.L)), B) for _ in range(9)]
+    dp = [oracle.scalarmul(b32(rnd.randrange(pyref.L)), B) for _ in range(5)]
+    sp[2] = oracle.identity(); dp[1] = oracle.decompress(b32(0))
+    ss = [b32(rnd.randrange(pyref.L)) for _ in range(9)]; ss[0] = b32(0); ss[1] = b32(2**255 - 1)
+    ds = [b32(rnd.randrange(pyref.L)) for _ in range(5)]
+    want = oracle.compress(oracle.msm("straus_vartime", ss + ds, sp + dp))
+    assert oracle.compress(oracle.precomputed_straus(ss, sp, ds, dp)) == want
+    # fewer static scalars than points: the tail is ignored; more: error; a None dynamic point: None
+    assert oracle.compress(oracle.precomputed_straus(ss[:4], sp, ds, dp)) == oracle.compress(oracle.msm("straus_vartime", ss[:4] + ds, sp[:4] + dp))
+    with pytest.raises(ValueError):
+        oracle.precomputed_straus(ss + [b32(1)], sp, ds, dp)
+    assert oracle.precomputed_straus(ss, sp, ds, dp[:2] + [None] + dp[3:]) is None
+    assert oracle.compress(oracle.precomputed_straus([], [], [], [])) == oracle.compress(oracle.identity())
+    # the reference's KAT: A_SCALAR * A_TIMES_BASEPOINT-style double-scalar result with B static, A dynamic
+    H = bytes.fromhex
+    a, b = H(kat["edwards"]["A_SCALAR"]["hex"]), H(kat["edwards"]["B_SCALAR"]["hex"])
+    A = oracle.decompress(H(kat["edwards"]["A_TIMES_BASEPOINT"]["hex"]))
+    assert oracle.compress(oracle.precomputed_straus([b], [B], [a], [A])) == H(kat["edwards"]["DOUBLE_SCALAR_MULT_RESULT"]["hex"])
+    # codecs
+    pts = [oracle.sub(oracle.add(oracle.double(q), q), oracle.double(q)) for q in sp + dp] + [oracle.identity()]
+    assert oracle.compress_batch(pts) == b"".join(oracle.compress(q) for q in pts)
+    assert oracle.compress_batch([]) == b""
+    assert oracle.ristretto_double_and_compress_batch(pts) == b"".join(oracle.ristretto_compress(oracle.double(q)) for q in pts)
+    encs = [H(h) for h in kat["ristretto"]["SMALL_MULTIPLES"]["hex"]]
+    small = [oracle.ristretto_decompress(e) for e in encs[:8]]
+    got = oracle.ristretto_double_and_compress_batch(small)
+    assert [got[32 * i:32 * i + 32] for i in range(8)] == [encs[2 * i] for i in range(8)]
