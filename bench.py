@@ -233,13 +233,14 @@ def run_msm(args, rank, world, local):
         sampler.start()
     launches0 = eng.launch_count()
     t0 = time.perf_counter()
+    call_ms = []
     for _ in range(args.steps):
         step()
         kernel_ms.append(eng.last_kernel_ms()[0])
+        call_ms.append(eng.last_call_ms())           # CUDA events on the engine's stream around the MSM call
     barrier()
     t1 = time.perf_counter()
     launches = eng.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     elapsed = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
@@ -250,10 +251,13 @@ def run_msm(args, rank, world, local):
         step(host=True)
     barrier()
     e0 = time.perf_counter()
+    e2e_call_ms = []
     for _ in range(args.steps):
         step(host=True)
+        e2e_call_ms.append(eng.last_call_ms())
     barrier()
     e1 = time.perf_counter()
+    clocks = sampler.stop() if rank == 0 else None        # sampled over both timed regions
     e2e_t = torch.tensor([e1 - e0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -276,12 +280,14 @@ def run_msm(args, rank, world, local):
         line = {
             "metric": "Pippenger MSM points/sec", "value": n_total * args.steps / elapsed, "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (radix 2^25.5), exact",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "exact integers: f64 limbs (radix 2^51, FP64 pipe) in the bucket kernel, u32 limbs (radix 2^25.5) elsewhere",
             "data": "synthetic: uniform 252-bit scalars, points t_i*B from the on-GPU fixed-base kernel",
             "config": {"workload": "pippenger_msm", "pairs_total": n_total, "pairs_per_gpu": n_local,
                        "point_format": "extended radix-2^51 limbs (160 B)", "window_bits": c,
                        "l2": "inputs (%.0f MB per GPU) exceed the 126 MB L2" % (algo_bytes / 1e6),
-                       "timing": "wall clock around K blocking C-ABI calls, bracketed by barrier + device sync, max over ranks",
+                       "timing": "value / ms_per_step: K blocking C-ABI calls bracketed by barrier + device sync, max over ranks; "
+                                 "device_ms_per_step: CUDA events on the engine's stream around each call (rank 0)",
+                       "device_ms_per_step": statistics.mean(call_ms), "e2e_device_ms_per_step": statistics.mean(e2e_call_ms),
                        "parity": "algebraic identity sum s_i(t_i B) == (sum s_i t_i)B checked at full size"},
             "e2e": {"value": n_total * args.steps / e2e_t, "unit": "points/s",
                     "h2d_bytes_per_step": n_local * 192, "d2h_bytes_per_step": 192 if world == 1 else nwin * 160 + 192},
@@ -386,13 +392,14 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
         sampler.start()
     l0 = eng.launch_count()
     t0 = time.perf_counter()
+    call_ms, e2e_call_ms = [], []
     for _ in range(steps):
         step()
         kernel_ms.append(eng.last_kernel_ms()[0])
+        call_ms.append(eng.last_call_ms())
     barrier()
     t1 = time.perf_counter()
     launches = eng.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     el = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
@@ -402,8 +409,10 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
     e0 = time.perf_counter()
     for _ in range(steps):
         step(host=True)
+        e2e_call_ms.append(eng.last_call_ms())
     barrier()
     e1 = time.perf_counter()
+    clocks = sampler.stop() if rank == 0 else None
     et = torch.tensor([e1 - e0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
@@ -416,9 +425,13 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
     return {
         "metric": "Ed25519 verify_batch signatures/sec", "value": n * world * steps / el, "unit": "sigs/s",
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": el / steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (radix 2^25.5), exact", "data": "synthetic: 59-byte messages, %d distinct keys, signatures made on the GPU (RFC 8032)" % min(nkeys, n),
+        "scaling": "weak", "vs_baseline": None, "dtype": "exact integers: f64 limbs (radix 2^51, FP64 pipe) in the bucket kernel, u32 limbs (radix 2^25.5) elsewhere", "data": "synthetic: 59-byte messages, %d distinct keys, signatures made on the GPU (RFC 8032)" % min(nkeys, n),
         "config": {"workload": "ed25519_verify_batch", "signatures_per_gpu": n, "message_bytes": 59, "distinct_keys": min(nkeys, n),
                    "verify_chunk": 64, "keys": "32-byte encodings, decompressed inside the call",
+                   "batch_size": batch_size or None,
+                   "timing": "value / ms_per_step: K blocking C-ABI calls bracketed by barrier + device sync, max over ranks; "
+                             "device_ms_per_step: CUDA events on the engine's stream around each call (rank 0)",
+                   "device_ms_per_step": statistics.mean(call_ms), "e2e_device_ms_per_step": statistics.mean(e2e_call_ms),
                    "l2": "inputs (%.0f MB) exceed the 126 MB L2" % (n * 155 / 1e6),
                    "replicas": "independent batches per GPU, no collective" if world > 1 else "single batch"},
         "e2e": {"value": n * world * steps / et, "unit": "sigs/s", "h2d_bytes_per_step": n * 155 + (n + 1) * 8, "d2h_bytes_per_step": 192},

@@ -30,6 +30,7 @@ int dalek_b200_init(int device, dalek_b200_ctx **out)
         cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_call0) != cudaSuccess || cudaEventCreate(&ctx->ev_call1) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
@@ -56,7 +57,7 @@ void dalek_b200_destroy(dalek_b200_ctx *ctx)
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
-    cudaEventDestroy(ctx->ev_join2);
+    cudaEventDestroy(ctx->ev_join2); cudaEventDestroy(ctx->ev_call0); cudaEventDestroy(ctx->ev_call1);
     for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev_grp[i]);
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2); cudaStreamDestroy(ctx->stream_copy); cudaStreamDestroy(ctx->stream3);
     delete ctx;
@@ -85,6 +86,13 @@ int dalek_b200_last_kernel_ms(const dalek_b200_ctx *ctx, float *ms, int *launche
     if (!ctx) return DALEK_E_INVALID_ARG;
     if (ms) *ms = ctx->last_kernel_ms;
     if (launches) *launches = ctx->last_kernel_launches;
+    return 0;
+}
+
+int dalek_b200_last_call_ms(const dalek_b200_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return DALEK_E_INVALID_ARG;
+    *ms = ctx->last_call_ms;
     return 0;
 }
 
@@ -166,6 +174,7 @@ static int msm_common(dalek_b200_ctx *ctx, const void *scalars, const void *poin
         return DALEK_E_INVALID_ARG;
     if (n >= (1ull << 31)) return DALEK_E_INVALID_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
     int rc;
     int c = msm_choose_window_bits(ctx, n);
     int nwin = msm_window_count_for_bits(c);
@@ -242,6 +251,7 @@ static int partial_common(dalek_b200_ctx *ctx, const void *scalars, const void *
         (point_fmt != DALEK_POINTS_COMPRESSED && point_fmt != DALEK_POINTS_EXTENDED) || n_local >= (1ull << 31))
         return DALEK_E_INVALID_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
     int rc;
     int c = msm_choose_window_bits(ctx, n_total);
     int nwin = msm_window_count_for_bits(c);

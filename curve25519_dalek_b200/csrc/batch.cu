@@ -547,6 +547,7 @@ static int verify_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t
                       const uint32_t *d_keys, size_t n, size_t batch, int32_t *verdicts)
 {
     int rc;
+    CallTimer timer(ctx);
     VerifyBufs b;
     if ((rc = verify_reserve(ctx, n, b))) return rc;
     CUDA_TRY(ctx, cudaMemsetAsync(b.flags, 0, 64, ctx->stream));
@@ -608,6 +609,7 @@ static int verify_host(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint
                        const uint8_t *pubkeys, size_t n, size_t batch, int32_t *verdicts)
 {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
     int rc;
     size_t mbytes = n ? (size_t)msg_offsets[n] : 0;
     if (n && msg_offsets[0] != 0) return DALEK_E_INVALID_ARG;

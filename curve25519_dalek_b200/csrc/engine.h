@@ -22,6 +22,7 @@ struct dalek_b200_ctx {
     cudaStream_t stream_copy = nullptr;
     cudaStream_t stream3 = nullptr;      // second hashing/transcript chain (odd verify pieces)
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+    cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;   // device span of the last hot-path call (CallTimer)
     cudaEvent_t ev_grp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // one per input piece
     std::string last_error;
     uint64_t launches = 0;
@@ -36,6 +37,7 @@ struct dalek_b200_ctx {
     long opt_field_f64 = 1;     // bucket kernel on the FP64 pipe (fe64.cuh) instead of IMAD.WIDE (fe.cuh)
     // timing of the dominant kernel in the last call
     float last_kernel_ms = 0.f;
+    float last_call_ms = 0.f;
     int last_kernel_launches = 0;
     // device workspaces (grown on demand, reused across calls)
     DevBuf scalars, points_in, points, digits, counts, offsets, sorted, buckets, red_a, red_b, red_c,
@@ -56,6 +58,21 @@ struct dalek_b200_ctx {
             return -3;                                                                           \
         }                                                                                        \
     } while (0)
+
+// Device time of one blocking call: an event on the main stream at entry, one after everything the call enqueued
+// (the other streams are joined into the main one before a call returns); read with dalek_b200_last_call_ms.
+struct CallTimer {
+    dalek_b200_ctx *ctx;
+    explicit CallTimer(dalek_b200_ctx *c) : ctx(c) { if (ctx) cudaEventRecord(ctx->ev_call0, ctx->stream); }
+    ~CallTimer()
+    {
+        if (!ctx) return;
+        float ms = 0.f;
+        if (cudaEventRecord(ctx->ev_call1, ctx->stream) == cudaSuccess && cudaEventSynchronize(ctx->ev_call1) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, ctx->ev_call0, ctx->ev_call1) == cudaSuccess)
+            ctx->last_call_ms = ms;
+    }
+};
 
 int ws_reserve(dalek_b200_ctx *ctx, DevBuf &b, size_t bytes);
 int pinned_reserve(dalek_b200_ctx *ctx, size_t bytes);

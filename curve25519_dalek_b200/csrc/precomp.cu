@@ -93,6 +93,7 @@ int dalek_b200_precomp_mixed_msm(dalek_b200_ctx *ctx, const dalek_b200_precomp *
         return DALEK_E_INVALID_ARG;                     // Edwards and Ristretto encodings do not mix
     if (n_static + n_dynamic >= (1ull << 31)) return DALEK_E_INVALID_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
     int rc;
     cudaStream_t st = ctx->stream;
     const int dkind = kind_of(dynamic_fmt);

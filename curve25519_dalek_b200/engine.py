@@ -35,6 +35,7 @@ def load_library():
     lib.dalek_b200_launch_count.argtypes = [vp]
     lib.dalek_b200_launch_count.restype = C.c_uint64
     lib.dalek_b200_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    lib.dalek_b200_last_call_ms.argtypes = [vp, C.POINTER(C.c_float)]
     for name in ("dalek_b200_edwards_vartime_msm", "dalek_b200_edwards_ct_msm", "dalek_b200_edwards_vartime_msm_dev"):
         getattr(lib, name).argtypes = [vp, vp, vp, C.c_int, sz, vp, vp]
     lib.dalek_b200_msm_window_count.argtypes = [vp, sz]
@@ -133,6 +134,12 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.dalek_b200_launch_count(self.h))
+
+    def last_call_ms(self):
+        """Device time (CUDA events on the engine's stream) of the last MSM / verify_batch call, in ms."""
+        ms = C.c_float()
+        self.lib.dalek_b200_last_call_ms(self.h, C.byref(ms))
+        return float(ms.value)
 
     def last_kernel_ms(self):
         ms, n = C.c_float(), C.c_int()

@@ -71,6 +71,10 @@ uint64_t dalek_b200_launch_count(const dalek_b200_ctx *ctx);
 /* Milliseconds (CUDA events on the context's stream) spent in the dominant kernel of the last
  * call (bucket accumulation for MSM calls), and that kernel's launch count in the last call. */
 int dalek_b200_last_kernel_ms(const dalek_b200_ctx *ctx, float *ms, int *launches);
+/* Milliseconds between CUDA events recorded on the context's stream at entry of the last MSM / verify_batch /
+ * precomputed-MSM call and after the last work it enqueued (all of the call's streams joined): the device time
+ * of that call, copies of host-buffer calls included. */
+int dalek_b200_last_call_ms(const dalek_b200_ctx *ctx, float *ms);
 
 /* -------- EdwardsPoint multiscalar multiplication --------------------------------------- */
 /*
