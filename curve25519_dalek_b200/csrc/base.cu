@@ -116,7 +116,7 @@ k_sign(const uint32_t *__restrict__ seeds, const uint8_t *__restrict__ msgs, con
     for (int k = 0; k < 8; k++) { pks[8 * i + k] = A[k]; sigs[16 * i + k] = R[k]; sigs[16 * i + 8 + k] = S[k]; }
 }
 
-static int ensure_table(dalek_b200_ctx *ctx)
+int base_table_ensure(dalek_b200_ctx *ctx)
 {
     if (ctx->base_table_ready) return 0;
     int rc;
@@ -137,7 +137,7 @@ int dalek_b200_edwards_mul_base_batch(dalek_b200_ctx *ctx, const uint8_t *scalar
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     int rc;
     cudaStream_t st = ctx->stream;
-    if ((rc = ensure_table(ctx))) return rc;
+    if ((rc = base_table_ensure(ctx))) return rc;
     if (!n) return 0;
     if ((rc = ws_reserve(ctx, ctx->scalars, n * 32))) return rc;
     if (out_limbs && (rc = ws_reserve(ctx, ctx->points_in, n * 160))) return rc;
@@ -160,7 +160,7 @@ int ed25519_b200_sign_batch_flat(dalek_b200_ctx *ctx, const uint8_t *seeds, cons
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     int rc;
     cudaStream_t st = ctx->stream;
-    if ((rc = ensure_table(ctx))) return rc;
+    if ((rc = base_table_ensure(ctx))) return rc;
     if (!n) return 0;
     size_t mbytes = (size_t)msg_offsets[n];
     if ((rc = ws_reserve(ctx, ctx->scalars, n * 32))) return rc;

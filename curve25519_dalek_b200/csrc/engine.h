@@ -112,6 +112,9 @@ int msm_combine_windows(dalek_b200_ctx *ctx, const ge_p3_raw *d_windows, int ran
 // ---- constant-time Straus (straus.cu) ----
 int straus_ct_msm(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points_pniels, size_t n,
                   MsmResult *d_result);
+// ---- fixed-base table (base.cu): 64 x 8 affine Niels entries (j+1) 16^i B, built once per context ----
+int base_table_ensure(dalek_b200_ctx *ctx);
+
 int ristretto_prepare_points(dalek_b200_ctx *ctx, const void *d_in, size_t n, void *d_out, int *d_bad);
 int ristretto_encode_result(dalek_b200_ctx *ctx, const MsmResult *d_res, uint32_t *d_enc);
 int ristretto_double_base(dalek_b200_ctx *ctx, const uint8_t *d_a, const uint8_t *d_b, const uint8_t G[32],

@@ -210,10 +210,11 @@ FE_HD uint32_t ge_decompress_affine(fe &x, fe &y, const uint32_t s[8])
 }
 
 // EdwardsPoint::compress (C/edwards.rs:564-617, edwards/affine.rs:71-75) -> 8 words
+template <int F64 = 0>
 FE_HD void ge_compress(uint32_t s[8], const ge_p3 &p)
 {
     fe recip, x, y;
-    fe_invert(recip, p.Z);
+    if (F64) fe_invert_f64(recip, p.Z); else fe_invert(recip, p.Z);
     fe_mul(x, p.X, recip);
     fe_mul(y, p.Y, recip);
     fe_tobytes_words(s, y);

@@ -72,6 +72,32 @@ FE_HD void ge64_padd(ge64_p3 &r, const ge64_p3 &p, const ge64_pniels &q, uint32_
     ge64_add_tail(r, a, b, c, D, neg);
 }
 
+// r = 2p (curve_models.rs:381-397 followed by :365-372).   4S + 4M, two balanced carries
+FE_HD void ge64_dbl(ge64_p3 &r, const ge64_p3 &p)
+{
+    FE64_ASSERT_SCALE(p.X, 1); FE64_ASSERT_SCALE(p.Y, 1); FE64_ASSERT_SCALE(p.Z, 1);
+    fe64 XX, YY, ZZ, XpY, XpY2, Yp, Ym, E, F;
+    fe64_sq(XX, p.X);
+    fe64_sq(YY, p.Y);
+    fe64_sq(ZZ, p.Z);
+    fe64_add(XpY, p.X, p.Y); fe64_carry(XpY, XpY);      // squaring needs scale < 2
+    fe64_sq(XpY2, XpY);
+    fe64_add(Yp, YY, XX);                               // 2
+    fe64_sub(Ym, YY, XX);                               // 2
+    fe64_sub(E, XpY2, Yp);                              // 3   (X+Y)^2 - Y^2 - X^2
+    fe64_add(F, ZZ, ZZ); fe64_sub(F, F, Ym);            // 4   2Z^2 - (Y^2 - X^2)
+    fe64_carry(F, F);                                   // 1
+    fe64_mul(r.X, E, F);                                // 3 x 1
+    fe64_mul(r.Y, Yp, Ym);                              // 2 x 2
+    fe64_mul(r.Z, Ym, F);                               // 2 x 1
+    fe64_mul(r.T, E, Yp);                               // 3 x 2
+}
+
+FE_HD void ge64_from_p3(ge64_p3 &o, const ge_p3 &p)
+{
+    fe64_from_fe(o.X, p.X); fe64_from_fe(o.Y, p.Y); fe64_from_fe(o.Z, p.Z); fe64_from_fe(o.T, p.T);
+}
+
 FE_HD void ge64_to_p3(ge_p3 &o, const ge64_p3 &p)
 {
     fe64_to_fe(o.X, p.X); fe64_to_fe(o.Y, p.Y); fe64_to_fe(o.Z, p.Z); fe64_to_fe(o.T, p.T);

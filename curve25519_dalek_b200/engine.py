@@ -59,6 +59,8 @@ def load_library():
     lib.dalek_b200_ristretto_decompress_batch.argtypes = [vp, vp, sz, vp, vp]
     lib.dalek_b200_edwards_compress_batch.argtypes = [vp, vp, sz, vp]
     lib.dalek_b200_ristretto_double_and_compress_batch.argtypes = [vp, vp, sz, vp]
+    lib.ed25519_b200_verify_each_flat.argtypes = [vp, vp, vp, vp, vp, sz, C.c_int, vp]
+    lib.ed25519_b200_verify_each_flat_dev.argtypes = [vp, vp, vp, vp, vp, sz, C.c_int, vp]
     lib.ed25519_b200_last_zs.argtypes = [vp, vp, sz]
     lib.dalek_b200_edwards_mul_base_batch.argtypes = [vp, vp, sz, vp, vp]
     lib.ed25519_b200_sign_batch_flat.argtypes = [vp, vp, vp, vp, sz, vp, vp]
@@ -245,6 +247,14 @@ class Engine:
         fn = self.lib.ed25519_b200_verify_batches_flat_dev if device_ptrs else self.lib.ed25519_b200_verify_batches_flat
         rc = self._check(fn(self.h, _ptr(msgs_flat), _ptr(offsets), _ptr(sigs), _ptr(pubkeys), n, batch_size, C.addressof(verdicts)))
         return rc, list(verdicts)[:nb]
+
+    def verify_each_flat(self, msgs_flat, offsets, sigs, pubkeys, n, strict=False, device_ptrs=False):
+        """n independent verifications: (rc, results) with results[i] the code of VerifyingKey::verify (or verify_strict)
+        for signature i alone; rc = 0 iff all are 0."""
+        res = (C.c_uint8 * max(n, 1))()
+        fn = self.lib.ed25519_b200_verify_each_flat_dev if device_ptrs else self.lib.ed25519_b200_verify_each_flat
+        rc = self._check(fn(self.h, _ptr(msgs_flat), _ptr(offsets), _ptr(sigs), _ptr(pubkeys), n, 1 if strict else 0, C.addressof(res)))
+        return rc, list(res)[:n]
 
     def last_zs(self, n):
         out = (C.c_uint8 * (16 * max(n, 1)))()

@@ -224,6 +224,18 @@ int ed25519_b200_verify_batches_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_fl
 int ed25519_b200_verify_batches_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat,
                                          const void *d_msg_offsets, const void *d_sigs,
                                          const void *d_pubkeys, size_t n, size_t batch_size, int32_t *verdicts);
+/* Many independent single verifications: results[i] = what VerifyingKey::from_bytes followed by
+ * verify (strict = 0, E/verifying.rs:167-175, :203-219) or verify_strict (strict = 1, E/verifying.rs:359-382)
+ * returns for signature i alone: 0 Ok, 1 Verify, 3 ScalarFormat, 4 PointDecompression.  R' = [s]B - [k]A is
+ * recomputed (RCompute, E/verifying.rs:496-557) and its ENCODING compared with the signature's R bytes, so --
+ * unlike verify_batch -- a non-canonical R is rejected; verify_strict also rejects small-order R or A.
+ * Returns 0 if every result is 0, 1 otherwise; negative on engine errors.  results: n bytes (host). */
+int ed25519_b200_verify_each_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint64_t *msg_offsets,
+                                  const uint8_t *sigs, const uint8_t *pubkeys, size_t n, int strict,
+                                  uint8_t *results);
+int ed25519_b200_verify_each_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat, const void *d_msg_offsets,
+                                      const void *d_sigs, const void *d_pubkeys, size_t n, int strict,
+                                      uint8_t *results);
 /* Debug/parity aid: the 16-byte z_i coefficients drawn in the last verify_batch call. */
 int ed25519_b200_last_zs(dalek_b200_ctx *ctx, uint8_t *zs_out, size_t n);
 

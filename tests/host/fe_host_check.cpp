@@ -136,4 +136,19 @@ int h_ge64_chain(uint8_t *out, const uint8_t *pts, const uint8_t *negs, int coun
     store_point(out, r);
     return 1;
 }
+// Q = 3P; 2^k * Q with ge64_dbl, then + Q through ge64_padd: returns compress((2^k + 1) * 3P)
+int h_ge64_dbl_chain(uint8_t *out, const uint8_t *pt, int k)
+{
+    ge_p3 q; if (!load_point(q, pt)) return 0;
+    ge_p3 q3; ge_dbl(q3, q); ge_add(q3, q3, q);                          // 3q, Z != 1
+    ge64_p3 acc; ge64_from_p3(acc, q3);
+    for (int i = 0; i < k; i++) ge64_dbl(acc, acc);
+    ge_pniels n; ge_p3_to_pniels(n, q3);
+    ge_pniels_packed pk; ge_pniels_pack(pk, n);
+    ge64_pniels n64; ge64_pniels_unpack(n64, pk);
+    ge64_padd(acc, acc, n64, 0);
+    ge_p3 r; ge64_to_p3(r, acc);
+    store_point(out, r);
+    return 1;
+}
 }

@@ -165,6 +165,11 @@ def test_fe64_model(host, oracle):
             pts[3] = ident; pts[4] = b32(0); pts[5] = b32(p - 1)
         negs = bytes(rnd.randrange(2) for _ in range(n))
         out = (C.c_uint8 * 32)()
+        for k in (0, 1, 2, 7) if trial < 2 else ():                     # doubling chain on the FP64 field
+            for pt in pts[:6]:
+                assert host.h_ge64_dbl_chain(out, pt, k) == 1
+                want = oracle.scalarmul(b32(3 * (2**k + 1)), oracle.decompress(pt))
+                assert bytes(out) == oracle.compress(want)
         assert host.h_ge64_chain(out, b"".join(pts), negs, n) == 1
         acc = oracle.identity()
         for k in range(n):
