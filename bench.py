@@ -339,7 +339,7 @@ def build_verify_inputs(eng, n, nkeys=1024):
     return flat, offs, np.frombuffer(sigs, dtype=np.uint8).copy(), np.frombuffer(pks, dtype=np.uint8).copy()
 
 
-def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkeys=1024, batch_size=0):
+def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkeys=1024, batch_size=0, each=False):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -358,8 +358,16 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
     d = [x.to(dev) for x in h]
     torch.cuda.synchronize()
 
+    each_res = np.zeros(n, dtype=np.uint8) if each else None
+
     def step(host=False):
         b = h if host else d
+        if each:            # one verdict per signature (VerifyingKey::verify semantics)
+            fn = eng.lib.ed25519_b200_verify_each_flat if host else eng.lib.ed25519_b200_verify_each_flat_dev
+            rc = fn(eng.h, b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(), n, 0, each_res.ctypes.data)
+            if rc != 0:
+                raise SystemExit("bench: verify_each rejected valid signatures (rc=%d)" % rc)
+            return
         if batch_size:      # independent batches of `batch_size`, one verdict each
             rc, verdicts = eng.verify_batches_flat(b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(), n, batch_size,
                                                    device_ptrs=not host)
@@ -380,6 +388,10 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
     # negative control: one flipped message bit must give Verify (1)
     d[0][59 * 777 + 3] ^= 1
     rc = eng.verify_batch_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, device_ptrs=True)
+    if each:
+        rc_e, res_e = eng.verify_each_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), 1024, device_ptrs=True)
+        if rc_e != 1 or [i for i, r in enumerate(res_e) if r] != [777]:
+            raise SystemExit("bench: verify_each did not single out the corrupted signature")
     d[0][59 * 777 + 3] ^= 1
     if rc != 1:
         raise SystemExit("bench: corrupted batch was not rejected (rc=%d)" % rc)
@@ -653,6 +665,9 @@ def main():
             # the same signatures as 2^14 independent batches of 256 (per-batch verdicts, one reference transcript each)
             v3 = run_verify(args, rank, world, local, eng=eng, steps=3, warmup=3, batch_size=256)
             line["verify_batch"]["batches_of_256"] = {k: v3[k] for k in ("value", "unit", "ms_per_step", "e2e")}
+            # one verdict per signature (VerifyingKey::verify semantics: R' recomputed and compared as bytes)
+            v4 = run_verify(args, rank, world, local, eng=eng, steps=2, warmup=1, each=True)
+            line["verify_each"] = {k: v4[k] for k in ("value", "unit", "ms_per_step", "e2e")}
             line["ristretto_double_base"] = run_double_base(eng)
     if rank == 0 and world == 1 and not args.no_extras:
         threads = 1

@@ -14,9 +14,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 H = bytes.fromhex
 OK, VERIFY, SCALARFMT, POINTDEC = 0, 1, 3, 4
-VERIFY_ALLOWED = {"low_order_R", "low_order_A", "low_order_component_R", "low_order_component_A", "low_order_residue",
-                  "non_canonical_A", "reencoded_k"}
-STRICT_ALLOWED = {"low_order_component_A", "low_order_component_R"}
+from test_oracle_ed25519 import STRICT_ALLOWED, VERIFY_ALLOWED   # the flag sets of tests/validation_criteria.rs:8-23
 
 
 @pytest.fixture(scope="module")
@@ -32,11 +30,6 @@ def flat(msgs):
     offs = np.zeros(len(msgs) + 1, dtype=np.uint64)
     offs[1:] = np.cumsum([len(m) for m in msgs])
     return np.frombuffer(b"".join(msgs) + b"\0", dtype=np.uint8).copy(), offs
-
-
-def test_allowed_flag_sets_match_the_oracle_tests():
-    import test_oracle_ed25519 as t
-    assert t.VERIFY_ALLOWED == VERIFY_ALLOWED and t.STRICT_ALLOWED == STRICT_ALLOWED
 
 
 @pytest.mark.parametrize("strict", [False, True])
