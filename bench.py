@@ -446,7 +446,8 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
                    "device_ms_per_step": statistics.mean(call_ms), "e2e_device_ms_per_step": statistics.mean(e2e_call_ms),
                    "l2": "inputs (%.0f MB) exceed the 126 MB L2" % (n * 155 / 1e6),
                    "replicas": "independent batches per GPU, no collective" if world > 1 else "single batch"},
-        "e2e": {"value": n * world * steps / et, "unit": "sigs/s", "h2d_bytes_per_step": n * 155 + (n + 1) * 8, "d2h_bytes_per_step": 192},
+        "e2e": {"value": n * world * steps / et, "unit": "sigs/s", "h2d_bytes_per_step": n * 155 + (n + 1) * 8,
+                "d2h_bytes_per_step": n if each else (4 * ((n + batch_size - 1) // batch_size) if batch_size else 192)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "whole call (155 B per signature)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": how,
