@@ -42,7 +42,10 @@ __device__ __forceinline__ uint32_t is_small_order(const ge_p3 &p)
     return ge_is_identity(q);
 }
 
-__global__ void __launch_bounds__(128, 2)
+#ifndef EACH_MIN_BLOCKS
+#define EACH_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, EACH_MIN_BLOCKS)
 k_verify_each(const uint8_t *__restrict__ msgs, const uint64_t *__restrict__ offs, const uint32_t *__restrict__ sigs,
               const uint32_t *__restrict__ keys, size_t n, int strict, const ge_niels_packed *__restrict__ base_row0,
               uint8_t *__restrict__ out)
