@@ -30,6 +30,7 @@ struct dalek_b200_ctx {
     long opt_window_bits = 0;
     long opt_verify_chunk = 64;
     long opt_host_chunks = 4;   // host-buffer MSM calls stream the pairs in this many chunks (copy/compute overlap)
+    long opt_precomp_tables = 1;   // precomputations of >= 4096 points keep 2^(cw) P tables (one bucket window, no doublings)
     long opt_double_base_comb = 1; // double-base batch through the shared-memory fixed-base comb (0 = per-pair Straus)
     long opt_dedupe_keys = 1;   // verify_batch decompresses every distinct public key once
     long opt_verify_pieces = 4; // host-buffer verify_batch calls stream the signatures in this many pieces
@@ -99,10 +100,11 @@ int msm_window_sums(dalek_b200_ctx *ctx, const uint32_t *d_scalars /* n x 8 word
 struct MsmResult { uint32_t compressed[8]; uint64_t limbs[20]; uint32_t is_identity; uint32_t pad; };
 // building blocks: one chunk of pairs into the buckets; then reduction (+ Horner + encode if d_result)
 int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n,
-                         int c, bool first, int active_windows = 0);
+                         int c, bool first, int active_windows = 0, size_t flat = 0);
 // window width for `n_short` scalars of `short_bits` bits plus `n_long` full-width scalars (verify_batch)
 int msm_choose_window_bits_mixed(const dalek_b200_ctx *ctx, size_t n_short, int short_bits, size_t n_long);
-int msm_reduce_finish(dalek_b200_ctx *ctx, int c, ge_p3_raw *d_windows, MsmResult *d_result);
+int msm_reduce_finish(dalek_b200_ctx *ctx, int c, ge_p3_raw *d_windows, MsmResult *d_result, bool flat = false);
+int msm_fill_identity(dalek_b200_ctx *ctx, ge_p3_raw *d_out, uint32_t count);
 // window sums + Horner + encode in one go (single-shard case)
 int msm_full(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n, int c,
              ge_p3_raw *d_windows, MsmResult *d_result);

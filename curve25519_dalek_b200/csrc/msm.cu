@@ -142,8 +142,9 @@ int msm_choose_window_bits_mixed(const dalek_b200_ctx *ctx, size_t n_short, int 
 
 // ------------------------------------------------------------------------------------------
 // digits + histogram.  entry = (int32 digit << 32) | rank
+// flat = 1: the digits of every window count into the buckets of window 0 (precomputed 2^(cw) P tables)
 __global__ void k_digits(const uint4 *__restrict__ scalars, size_t n, int c, int nwin, uint32_t nbuckets,
-                         uint32_t *__restrict__ counts, uint64_t *__restrict__ entries)
+                         uint32_t *__restrict__ counts, uint64_t *__restrict__ entries, int flat)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -166,7 +167,7 @@ __global__ void k_digits(const uint4 *__restrict__ scalars, size_t n, int c, int
         uint32_t rank = 0;
         if (d != 0) {
             uint32_t bkt = (uint32_t)(d < 0 ? -d : d) - 1;
-            rank = atomicAdd(&counts[(size_t)w * nbuckets + bkt], 1u);
+            rank = atomicAdd(&counts[(flat ? (size_t)0 : (size_t)w * nbuckets) + bkt], 1u);
         }
         entries[(size_t)w * n + i] = ((uint64_t)(uint32_t)d << 32) | rank;
     }
@@ -230,8 +231,9 @@ __global__ void __launch_bounds__(1024) k_scan_apply(const uint32_t *__restrict_
 // Launched per group of windows [w0, w1) sized so that the group's slice of `sorted` stays in L2: the
 // 4-byte scattered writes of one 32-byte sector then merge in L2 instead of each costing a DRAM
 // read-modify-write.
+// flat != 0: one bucket window; the stored index is w * flat + i, the position of 2^(cw) P_i in the point table
 __global__ void k_scatter(const uint64_t *__restrict__ entries, const uint32_t *__restrict__ offsets, size_t n,
-                          int w0, int w1, uint32_t nbuckets, uint32_t *__restrict__ sorted)
+                          int w0, int w1, uint32_t nbuckets, uint32_t *__restrict__ sorted, size_t flat /* table stride, 0 = off */)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -240,8 +242,13 @@ __global__ void k_scatter(const uint64_t *__restrict__ entries, const uint32_t *
         int32_t d = (int32_t)(e >> 32);
         if (d == 0) continue;
         uint32_t neg = d < 0, bkt = (uint32_t)(neg ? -d : d) - 1;
-        uint32_t pos = offsets[(size_t)w * nbuckets + bkt] + (uint32_t)e;
-        sorted[(size_t)w * n + pos] = (uint32_t)i | (neg << 31);
+        if (flat) {
+            uint32_t pos = offsets[bkt] + (uint32_t)e;
+            sorted[pos] = (uint32_t)((size_t)w * flat + i) | (neg << 31);
+        } else {
+            uint32_t pos = offsets[(size_t)w * nbuckets + bkt] + (uint32_t)e;
+            sorted[(size_t)w * n + pos] = (uint32_t)i | (neg << 31);
+        }
     }
 }
 
@@ -627,14 +634,18 @@ k_combine(const ge_p3_raw *__restrict__ windows, int ranks, int nwin, int c, Msm
 // MSM must use the same window width c.
 // `active_windows` > 0 promises that every scalar of this chunk is below 2^(c * active_windows - 1): digits are
 // extracted, sorted and accumulated for the low `active_windows` windows only (verify_batch: the 128-bit z_i).
+// `flat` (a table stride): d_points holds nwin tables of `flat` points, table w = 2^(cw) P_i (precomp.cu); every digit then goes into ONE
+// bucket window, so the reduction handles 2^(c-1) buckets instead of nwin times as many and no doubling is left
+// (pair with msm_reduce_finish(..., flat = true)).
 int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n,
-                         int c, bool first, int active_windows)
+                         int c, bool first, int active_windows, size_t flat)
 {
-    const int nwin = msm_window_count_for_bits(c);
-    const int nact = active_windows > 0 && active_windows < nwin ? active_windows : nwin;
+    const int nwin_d = msm_window_count_for_bits(c);               // digit windows
+    const int nact = active_windows > 0 && active_windows < nwin_d ? active_windows : nwin_d;
+    const int nwin = flat ? 1 : nwin_d;                            // bucket windows
     const uint32_t nb = 1u << (c - 1);
     const size_t total_buckets = (size_t)nwin * nb;
-    const uint32_t task_len = msm_task_len(n, nact, nb);
+    const uint32_t task_len = flat ? msm_task_len(n * (size_t)nact, 1, nb) : msm_task_len(n, nact, nb);
     const size_t max_tasks = total_buckets + (std::max<size_t>(1, n) * nact) / task_len + 1;
     const size_t max_heavy = (std::max<size_t>(1, n) * nact) / task_len + 1;
     const uint32_t parts = (nb + SCAN_PART - 1) / SCAN_PART;
@@ -667,7 +678,7 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
     CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (total_buckets + 1) * 4, st));
     CUDA_TRY(ctx, cudaMemsetAsync(t_hist, 0, 2 * TASK_BINS * 4, st));
     if (n) {
-        k_digits<<<cdiv(n, 256), 256, 0, st>>>((const uint4 *)d_scalars, n, c, nact, nb, counts, entries);
+        k_digits<<<cdiv(n, 256), 256, 0, st>>>((const uint4 *)d_scalars, n, c, nact, nb, counts, entries, flat ? 1 : 0);
         ctx->launches++;
     }
     k_scan_partial<<<nwin * parts, 1024, 0, st>>>(counts, nb, parts, part_sums);
@@ -686,7 +697,7 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
     if (n) {
         const int wg = (int)std::max<size_t>(1, std::min<size_t>((size_t)nact, ((size_t)64 << 20) / (n * 4)));
         for (int w0 = 0; w0 < nact; w0 += wg) {
-            k_scatter<<<cdiv(n, 256), 256, 0, st>>>(entries, offsets, n, w0, std::min(nact, w0 + wg), nb, sorted);
+            k_scatter<<<cdiv(n, 256), 256, 0, st>>>(entries, offsets, n, w0, std::min(nact, w0 + wg), nb, sorted, flat);
             ctx->launches++;
         }
     }
@@ -708,9 +719,12 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
 }
 
 // Bucket reduction of all windows, and (if d_result) the Horner over windows + encoding.
-int msm_reduce_finish(dalek_b200_ctx *ctx, int c, ge_p3_raw *d_windows, MsmResult *d_result)
+// flat: the buckets are the single window filled by msm_accumulate_chunk(..., flat = true): d_windows[0] is already
+// the whole sum and d_result (if given) needs no doubling.
+int msm_reduce_finish(dalek_b200_ctx *ctx, int c, ge_p3_raw *d_windows, MsmResult *d_result, bool flat)
 {
-    const int nwin = msm_window_count_for_bits(c);
+    const int nwin = flat ? 1 : msm_window_count_for_bits(c);
+    const int desc_key = c + (flat ? 64 : 0);
     const uint32_t nb = 1u << (c - 1);
     cudaStream_t st = ctx->stream;
     int rc;
@@ -758,11 +772,11 @@ int msm_reduce_finish(dalek_b200_ctx *ctx, int c, ge_p3_raw *d_windows, MsmResul
         if ((rc = ws_reserve(ctx, ctx->sum_desc, (n1 + n2) * sizeof(uint2)))) return rc;
         if ((rc = ws_reserve(ctx, ctx->sum_part, n1 * sizeof(ge_p3_raw)))) return rc;
         uint2 *dd1 = (uint2 *)ctx->sum_desc.p, *dd2 = dd1 + n1;
-        if (ctx->sum_desc_c != c) {
+        if (ctx->sum_desc_c != desc_key) {
             CUDA_TRY(ctx, cudaMemcpyAsync(dd1, d1.data(), n1 * sizeof(uint2), cudaMemcpyHostToDevice, st));
             CUDA_TRY(ctx, cudaMemcpyAsync(dd2, d2.data(), n2 * sizeof(uint2), cudaMemcpyHostToDevice, st));
             CUDA_TRY(ctx, cudaStreamSynchronize(st));       // d1/d2 are host temporaries (rare: once per width)
-            ctx->sum_desc_c = c;
+            ctx->sum_desc_c = desc_key;
         }
         ge_p3_raw *parts = (ge_p3_raw *)ctx->sum_part.p;
         k_plain_sum<<<(unsigned)n1, 128, 0, st>>>(pool, dd1, parts);
@@ -775,6 +789,24 @@ int msm_reduce_finish(dalek_b200_ctx *ctx, int c, ge_p3_raw *d_windows, MsmResul
         k_combine<<<1, 32, 0, st>>>(d_windows, 1, nwin, c, d_result);
         ctx->launches++;
     }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_fill_identity(ge_p3_raw *__restrict__ out, uint32_t count)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    ge_p3 id; ge_p3_identity(id);
+    ge_p3_raw r; ge_p3_store_raw(r, id);
+    out[i] = r;
+}
+
+int msm_fill_identity(dalek_b200_ctx *ctx, ge_p3_raw *d_out, uint32_t count)
+{
+    if (!count) return 0;
+    k_fill_identity<<<cdiv(count, 128), 128, 0, ctx->stream>>>(d_out, count);
+    ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }

@@ -147,3 +147,51 @@ def test_precomputed_large_reuse(eng, oracle):
         total = sum(int.from_bytes(s[i].tobytes(), "little") * tv[i] for i in range(n)) % pyref.L
         assert bytes(out) == oracle.compress(oracle.scalarmul(b32(total), B))
     pre.close()
+
+
+@pytest.mark.parametrize("tables", [1, 0])
+def test_precomputed_window_tables(eng, oracle, tables):
+    """>= 4096 static points keep the tables 2^(c w) P_i (one bucket window, no doublings).  With and without them:
+    full and partial static scalar lists, dynamic points of their own width, edge scalars, all against
+    sum b_j (t_j B) + sum a_i (u_i B) = (sum b_j t_j + sum a_i u_i) B computed by the oracle."""
+    import numpy as np
+    import curve25519_dalek_b200 as pkg
+    n, nd = 5000, 37
+    rng = np.random.Generator(np.random.PCG64(21))
+    t = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); t[:, 31] &= 0x0F
+    t[7] = 0; t[8] = 0; t[8, 0] = 1                                  # identity and B itself among the static points
+    u = rng.integers(0, 256, size=(nd, 32), dtype=np.uint8); u[:, 31] &= 0x0F
+    limbs, _ = eng.mul_base_batch(t, n, want_compressed=False)
+    dlimbs, dcomp = eng.mul_base_batch(u, nd)
+    tv = [int.from_bytes(t[i].tobytes(), "little") for i in range(n)]
+    uv = [int.from_bytes(u[i].tobytes(), "little") for i in range(nd)]
+    B = oracle.basepoint()
+    eng.set_option("precomp_tables", tables)
+    try:
+        pre = pkg.VartimeEdwardsPrecomputation((limbs, n), engine=eng, fmt=pkg.POINTS_EXTENDED)
+    finally:
+        eng.set_option("precomp_tables", 1)
+    for ns in (n, 4097, 1):
+        b = rng.integers(0, 256, size=(ns, 32), dtype=np.uint8); b[:, 31] &= 0x1F
+        b[0] = 255; b[0, 31] = 0x7F                                   # 2^255 - 1
+        if ns > 3:
+            b[1] = 0; b[2] = 0; b[2, 0] = 1
+        a = rng.integers(0, 256, size=(nd, 32), dtype=np.uint8); a[:, 31] &= 0x0F
+        bv = [int.from_bytes(b[i].tobytes(), "little") for i in range(ns)]
+        av = [int.from_bytes(a[i].tobytes(), "little") for i in range(nd)]
+        for dyn in (False, True):
+            total = sum(x * y for x, y in zip(bv, tv)) + (sum(x * y for x, y in zip(av, uv)) if dyn else 0)
+            want = oracle.compress(oracle.scalarmul(b32(total % pyref.L), B))
+            out = (C.c_uint8 * 32)()
+            rc = eng.lib.dalek_b200_precomp_mixed_msm(eng.h, pre.h, b.ctypes.data, ns, a.ctypes.data if dyn else None,
+                                                      C.cast(dlimbs, C.c_void_p).value if dyn else None, 1, nd if dyn else 0,
+                                                      C.addressof(out), None)
+            assert rc == 0 and bytes(out) == want, (tables, ns, dyn)
+    # compressed dynamic points, one of them undecodable -> None
+    enc = bytearray(dcomp); enc[32 * 5:32 * 6] = b32(2)
+    out = (C.c_uint8 * 32)()
+    a = rng.integers(0, 256, size=(nd, 32), dtype=np.uint8); a[:, 31] &= 0x0F
+    b = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); b[:, 31] &= 0x0F
+    ebuf = (C.c_uint8 * len(enc)).from_buffer(enc)
+    assert eng.lib.dalek_b200_precomp_mixed_msm(eng.h, pre.h, b.ctypes.data, n, a.ctypes.data, C.addressof(ebuf), 0, nd, C.addressof(out), None) == 1
+    pre.close()
