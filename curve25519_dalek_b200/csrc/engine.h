@@ -30,7 +30,7 @@ struct dalek_b200_ctx {
     long opt_window_bits = 0;
     long opt_verify_chunk = 64;
     long opt_host_chunks = 4;   // host-buffer MSM calls stream the pairs in this many chunks (copy/compute overlap)
-    long opt_precomp_tables = 1;   // precomputations of >= 4096 points keep 2^(cw) P tables (one bucket window, no doublings)
+    long opt_precomp_tables = 0;   // 1: precomputations of >= 4096 points also keep 2^(cw) P tables (one bucket window, no doublings)
     long opt_double_base_comb = 1; // double-base batch through the shared-memory fixed-base comb (0 = per-pair Straus)
     long opt_dedupe_keys = 1;   // verify_batch decompresses every distinct public key once
     long opt_verify_pieces = 4; // host-buffer verify_batch calls stream the signatures in this many pieces

@@ -5,10 +5,13 @@
 // The reference precomputes width-8 NAF tables of the static points so that repeated calls skip that work.
 // Here the precomputation is what the bucket MSM can reuse between calls, RESIDENT in HBM:
 //   * the static points decoded and converted to packed (projective) Niels form, and
-//   * for >= 4096 points, the tables 2^(c w) P_i for every window w of the width c chosen at construction, as affine
-//     Niels points (96 B each, 1.7 GB for 2^20 points at c = 16).  With them a digit of window w selects from table
-//     w and ALL windows share one set of 2^(c-1) buckets: the reduction shrinks by the window count, the final
-//     Horner (256 sequential doublings) disappears, and the additions are mixed (7M instead of 8M).
+//   * with the option "precomp_tables" and >= 4096 points, the tables 2^(c w) P_i for every window w of the width c
+//     chosen at construction, as affine Niels points (96 B each, 1.7 GB for 2^20 points at c = 16).  With them a
+//     digit of window w selects from table w and ALL windows share one set of 2^(c-1) buckets: the reduction shrinks
+//     by the window count, the final Horner (256 sequential doublings) disappears, and the additions are mixed (7M
+//     instead of 8M).  Measured on B200 (tools/sweep_precomp.py, 2^20 points): 3.26-3.35 ms per call against
+//     3.33-3.44 ms without the tables -- the bucket kernel loses to 1.7 GB of random gathers (1.99 ms against
+//     1.59 ms with the 128 MB point array that stays in L2) most of what the tail saves.  Hence off by default.
 // A call moves only scalars (32 B per static point instead of 192 B).  Dynamic terms go through the ordinary
 // multi-window path and the two partial results are added.  The result is the same group element as the
 // reference's (tests compare canonical encodings).

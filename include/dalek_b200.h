@@ -63,7 +63,9 @@ const char *dalek_b200_last_error(const dalek_b200_ctx *ctx);
  * on the FP64-pipe field, default; 0 = IMAD.WIDE field), "host_chunks" (1..8, host-buffer MSM calls
  * stream their input in this many chunks, default 4), "verify_pieces" (1..8, same for verify_batch,
  * default 4), "decompress_f64" (1 = square-root exponentiation of decompression on the FP64 field, default), "dedupe_keys" (1 = decompress every distinct public key once and give it one MSM term,
- * default), "double_base_comb" (1 = fixed-base comb for double-base batches of >= 4096 pairs, default).
+ * default), "double_base_comb" (1 = fixed-base comb for double-base batches of >= 4096 pairs, default),
+ * "precomp_tables" (1 = precomputations of >= 4096 points also keep the 2^(cw) P window tables; default 0:
+ * measured, the 1.7 GB of randomly gathered table entries cost the bucket kernel what the shorter tail saves).
  * Returns 0 or DALEK_E_INVALID_ARG. */
 int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
@@ -127,7 +129,9 @@ int dalek_b200_edwards_msm_combine(dalek_b200_ctx *ctx, const uint64_t *windows,
 /* -------- VartimePrecomputedMultiscalarMul ---------------------------------
  * C/traits.rs:290-406; VartimeEdwardsPrecomputation C/edwards.rs:1038-1076, VartimeRistrettoPrecomputation
  * C/ristretto.rs:1004-1049 (serial backend: precomputed_straus.rs:33-127).  The static points are decoded
- * and converted once and stay resident in device memory; later calls send scalars only.
+ * and converted once and stay resident in device memory; later calls send scalars only.  With the option
+ * "precomp_tables" the tables 2^(c w) P_i of every window are kept too (96 B x windows per point, e.g. 1.7 GB for
+ * 2^20 points), so that all windows share one bucket set and the final doublings disappear.
  *
  * new (traits.rs:297-300): static_points in format DALEK_POINTS_* (RISTRETTO makes a Ristretto
  * precomputation: Ristretto encodings in and out).  DALEK_NONE if an encoded static point does not decode. */
