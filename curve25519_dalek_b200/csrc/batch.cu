@@ -36,14 +36,11 @@ k_hram(const uint8_t *__restrict__ msgs, const uint64_t *__restrict__ offs, cons
     uint32_t R[8], A[8], s[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) { R[k] = sigs[16 * i + k]; s[k] = sigs[16 * i + 8 + k]; A[k] = keys[8 * i + k]; }
-    sha512_state st;
-    sha512_init(st);
-    sha512_update_words(st, R);
-    sha512_update_words(st, A);
-    uint64_t lo = offs[i], hi = offs[i + 1];
-    sha512_update(st, msgs + lo, (size_t)(hi - lo));
     uint32_t dig[16];
-    sha512_final_words(st, dig);
+    {
+        const uint64_t lo = offs[i], hi = offs[i + 1];
+        sha512_ram(dig, R, A, msgs + lo, (size_t)(hi - lo));
+    }
 #pragma unroll
     for (int k = 0; k < 16; k++) hrams[16 * i + k] = dig[k];
     uint32_t h[8];

@@ -45,6 +45,7 @@ struct dalek_b200_ctx {
         red_d, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums, msg_offs, sum_desc, sum_part, key_table, key_acc, task_order, sig_status, misc6;
     int sum_desc_c = -1;
     bool base_table_ready = false;
+    bool comb_attr_set = false;     // cudaFuncAttributeMaxDynamicSharedMemorySize set for the comb kernel on this device
     // pinned host staging
     void *h_pinned = nullptr;
     size_t h_pinned_cap = 0;

@@ -116,6 +116,80 @@ __device__ __forceinline__ void sha512_final_words(sha512_state &s, uint32_t out
     }
 }
 
+// SHA-512(R || A || M) with the blocks assembled in registers (static word indices, no staging buffer in local
+// memory): the hash of batch.rs:179-191 / verifying.rs:515-523, one call per signature.  R, A: eight little-endian
+// words each (their bytes in order); M: `len` bytes at `msg` (any alignment).  dig: 16 LE words.
+__device__ __forceinline__ void sha512_compress_regs(uint64_t h[8], uint64_t w[16])
+{
+    uint64_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll 1
+    for (int r = 0; r < 80; r += 16) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (r) {
+                uint64_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+                uint64_t s0 = ror64(w15, 1) ^ ror64(w15, 8) ^ (w15 >> 7);
+                uint64_t s1 = ror64(w2, 19) ^ ror64(w2, 61) ^ (w2 >> 6);
+                w[i] = w[i] + s0 + w[(i + 9) & 15] + s1;
+            }
+            uint64_t S1 = ror64(e, 14) ^ ror64(e, 18) ^ ror64(e, 41);
+            uint64_t ch = (e & f) ^ (~e & g);
+            uint64_t t1 = hh + S1 + ch + SHA512_K[r + i] + w[i];
+            uint64_t S0 = ror64(a, 28) ^ ror64(a, 34) ^ ror64(a, 39);
+            uint64_t mj = (a & b) ^ (a & c) ^ (b & c);
+            uint64_t t2 = S0 + mj;
+            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
+__device__ __forceinline__ void sha512_ram(uint32_t dig[16], const uint32_t R[8], const uint32_t A[8], const uint8_t *__restrict__ msg,
+                                           size_t len)
+{
+    uint64_t h[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+                     0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+    const size_t total = 64 + len;                               // message bytes of the hash input
+    const size_t nblocks = (total + 1 + 16 + 127) / 128;
+    // big-endian 64-bit word from two LE 32-bit words holding 8 consecutive bytes
+#define SHA_BE64(lo, hi) (((uint64_t)__byte_perm((lo), 0, 0x0123) << 32) | (uint64_t)__byte_perm((hi), 0, 0x0123))
+#pragma unroll 1
+    for (size_t blk = 0; blk < nblocks; blk++) {
+        uint64_t w[16];
+        const size_t base = blk * 128;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const size_t off = base + 8 * j;                     // first input byte of this word
+            uint64_t v;
+            if (blk == 0 && j < 4) v = SHA_BE64(R[2 * j], R[2 * j + 1]);
+            else if (blk == 0 && j < 8) v = SHA_BE64(A[2 * (j - 4)], A[2 * (j - 4) + 1]);
+            else {
+                v = 0;
+                if (off + 8 <= total) {                          // eight message bytes
+#pragma unroll
+                    for (int b = 0; b < 8; b++) v = (v << 8) | (uint64_t)msg[off - 64 + b];
+                } else if (off <= total) {                       // tail of the message, then the 0x80 marker
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        const size_t q = off + b;
+                        const uint64_t byte = q < total ? (uint64_t)msg[q - 64] : (q == total ? 0x80u : 0u);
+                        v = (v << 8) | byte;
+                    }
+                }
+            }
+            w[j] = v;
+        }
+        if (blk == nblocks - 1) w[15] = (uint64_t)total * 8;     // bit length (w[14] stays 0: inputs < 2^61 bytes)
+        sha512_compress_regs(h, w);
+    }
+#undef SHA_BE64
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        dig[2 * i] = __byte_perm((uint32_t)(h[i] >> 32), 0, 0x0123);
+        dig[2 * i + 1] = __byte_perm((uint32_t)h[i], 0, 0x0123);
+    }
+}
+
 // ---------------------------------------------------------------- Keccak-f[1600]
 static __device__ __constant__ uint64_t KECCAK_RC[24] = {
     0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,

@@ -68,14 +68,9 @@ k_verify_each(const uint8_t *__restrict__ msgs, const uint64_t *__restrict__ off
     // k = SHA-512(R || A || M) mod l  (verifying.rs:515-523)
     uint32_t h[8];
     {
-        sha512_state st;
-        sha512_init(st);
-        sha512_update_words(st, R);
-        sha512_update_words(st, Ak);
-        uint64_t lo = offs[i], hi = offs[i + 1];
-        sha512_update(st, msgs + lo, (size_t)(hi - lo));
         uint32_t dig[16];
-        sha512_final_words(st, dig);
+        const uint64_t lo = offs[i], hi = offs[i + 1];
+        sha512_ram(dig, R, Ak, msgs + lo, (size_t)(hi - lo));
         sc_reduce512(h, dig);
     }
     ge_p3 A;

@@ -328,10 +328,9 @@ static int double_base_setup(dalek_b200_ctx *ctx, const uint8_t G[32], const uin
     CUDA_TRY(ctx, cudaMemsetAsync(plan.d_status, 0, 4, st));
     const bool comb = ctx->opt_double_base_comb && n >= 4096;     // the table build only pays off for a real batch
     if (comb) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!ctx->comb_attr_set) {                               // per context: the attribute is per device
             CUDA_TRY(ctx, cudaFuncSetAttribute(k_double_base_comb<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)comb_bytes));
-            attr_set = true;
+            ctx->comb_attr_set = true;
         }
         k_comb_tables<<<8, 128, 0, st>>>(d_gh, d_comb, plan.d_status);
         plan.table = d_comb; plan.variant = 1; plan.smem = comb_bytes;
