@@ -71,6 +71,7 @@ int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value)
     if (!strcmp(name, "window_bits")) { if (value != 0 && (value < 4 || value > 20)) return DALEK_E_INVALID_ARG; ctx->opt_window_bits = value; return 0; }
     if (!strcmp(name, "host_chunks")) { if (value < 1 || value > 8) return DALEK_E_INVALID_ARG; ctx->opt_host_chunks = value; return 0; }
     if (!strcmp(name, "decompress_f64")) { ctx->opt_decompress_f64 = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "trace")) { ctx->opt_trace = value ? 1 : 0; return 0; }
     if (!strcmp(name, "precomp_tables")) { ctx->opt_precomp_tables = value ? 1 : 0; return 0; }
     if (!strcmp(name, "double_base_comb")) { ctx->opt_double_base_comb = value ? 1 : 0; return 0; }
     if (!strcmp(name, "dedupe_keys")) { ctx->opt_dedupe_keys = value ? 1 : 0; return 0; }

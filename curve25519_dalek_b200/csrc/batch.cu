@@ -375,8 +375,10 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
         k_hram<<<cdiv(cnt, 128), 128, 0, st>>>(d_msgs, d_offs + i0, d_sigs + 16 * i0, d_keys + 8 * i0, cnt, b.hrams + 16 * i0,
                                                b.hs + 8 * i0, b.flags, b.bad_s + i0);
         size_t nchunks = (cnt + chunk - 1) / chunk;
+        trace_mark(ctx, "hram done (hash stream)", st);
         k_transcript<<<cdiv(nchunks, 64), 64, 0, st>>>(b.hrams + 16 * i0, d_sigs + 16 * i0, cnt, chunk, b.zs + 4 * i0);
         ctx->launches += 2;
+        trace_mark(ctx, "transcript done (hash stream)", st);
     }
     ge_niels_packed *points_A = b.points + 1;
     if (ctx->opt_decompress_f64)
@@ -384,6 +386,7 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
     else
         k_prep_R<0><<<cdiv(cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, cnt, b.points + 1 + n + i0, i0 == 0 ? b.points : nullptr, b.flags, b.bad_r + i0);
     ctx->launches++;
+    trace_mark(ctx, "prep_R done (decompress stream)", st2);
     if (ctx->opt_dedupe_keys) {
         // keys first seen in this piece are uniq[counters[piece] .. counters[1 + piece])  (counters[15] = 0 for piece 0)
         const uint32_t *lo = piece ? b.counters + piece : b.counters + 15, *hi = b.counters + 1 + piece;
@@ -403,7 +406,9 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
         k_coeffs<<<cdiv(cnt, 128), 128, 0, st>>>(b.zs + 4 * i0, d_sigs + 16 * i0, b.hs + 8 * i0, cnt, b.scalars + 8 * (1 + n + i0),
                                                  out_zh, b.zsprod + 8 * i0);
         ctx->launches++;
+        trace_mark(ctx, "coeffs done (hash stream)", st);
     }
+    trace_mark(ctx, "keys done (decompress stream)", st2);
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
@@ -420,6 +425,7 @@ static int verify_join(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, int p
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join2, 0));
     if ((rc = pinned_reserve(ctx, sizeof(MsmResult) + 128))) return rc;
     *nkeys = n;
+    trace_mark(ctx, "front end joined", st);
     if (ctx->opt_dedupe_keys && n) {
         // the number of distinct keys sizes the MSM: one small read-back in the middle of the call
         uint32_t *hk = (uint32_t *)((char *)ctx->h_pinned + sizeof(MsmResult) + 64);
@@ -456,6 +462,7 @@ static int verify_equation(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, s
             ctx->launches += 2;
         }
     }
+    trace_mark(ctx, "sums and per-key scalars done", st);
     // the z_i are 128-bit (batch.rs:224-229): their terms only populate the low windows
     const size_t nlong = merged ? nkeys + 1 : cnt + 1;
     const int c = msm_choose_window_bits_mixed(ctx, cnt, 128, nlong);
@@ -468,8 +475,11 @@ static int verify_equation(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, s
         if ((rc = msm_accumulate_chunk(ctx, b.scalars, b.points, PK_NIELS, 1, c, true))) return rc;
         if (cnt && (rc = msm_accumulate_chunk(ctx, b.scalars + 8 * (1 + lo), b.points + 1 + lo, PK_NIELS, cnt, c, false))) return rc;
     }
+    trace_mark(ctx, "key chunk accumulated", st);
     if (cnt && (rc = msm_accumulate_chunk(ctx, b.scalars + 8 * (1 + n + lo), b.points + 1 + n + lo, PK_NIELS, cnt, c, false, (128 + c) / c))) return rc;
+    trace_mark(ctx, "R chunk accumulated", st);
     if ((rc = msm_reduce_finish(ctx, c, (ge_p3_raw *)ctx->misc0.p, (MsmResult *)ctx->result.p))) return rc;
+    trace_mark(ctx, "reduced and combined", st);
     MsmResult *h = (MsmResult *)ctx->h_pinned;
     CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->result.p, sizeof(MsmResult), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -490,6 +500,7 @@ static int verify_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, int p
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
+    trace_dump(ctx);
     // error precedence follows the reference: VerifyingKey::from_bytes happens before verify_batch
     // can be called (PointDecompression); then s canonicity (batch.rs:208-211); then R / equation.
     if (hflags[FLAG_BAD_A]) return ED25519_ERR_POINT_DECOMPRESSION;

@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "ge.cuh"
@@ -30,6 +32,7 @@ struct dalek_b200_ctx {
     long opt_window_bits = 0;
     long opt_verify_chunk = 64;
     long opt_host_chunks = 4;   // host-buffer MSM calls stream the pairs in this many chunks (copy/compute overlap)
+    long opt_trace = 0;            // 1: print a per-stage device timeline of verify_batch calls to stderr (diagnostics)
     long opt_precomp_tables = 0;   // 1: precomputations of >= 4096 points also keep 2^(cw) P tables (one bucket window, no doublings)
     long opt_double_base_comb = 1; // double-base batch through the shared-memory fixed-base comb (0 = per-pair Straus)
     long opt_dedupe_keys = 1;   // verify_batch decompresses every distinct public key once
@@ -50,6 +53,7 @@ struct dalek_b200_ctx {
     void *h_pinned = nullptr;
     size_t h_pinned_cap = 0;
     size_t last_zs_n = 0;
+    std::vector<std::pair<const char *, cudaEvent_t>> trace;   // stage marks of the current call (opt_trace)
 };
 
 #define CUDA_TRY(ctx, expr)                                                                      \
@@ -75,6 +79,28 @@ struct CallTimer {
             ctx->last_call_ms = ms;
     }
 };
+
+// diagnostics: timestamp `name` on `st` (relative to the CallTimer start), printed by trace_dump
+inline void trace_mark(dalek_b200_ctx *ctx, const char *name, cudaStream_t st)
+{
+    if (!ctx->opt_trace) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    ctx->trace.push_back({name, e});
+}
+inline void trace_dump(dalek_b200_ctx *ctx)
+{
+    if (!ctx->opt_trace) return;
+    cudaDeviceSynchronize();
+    for (auto &m : ctx->trace) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev_call0, m.second);
+        fprintf(stderr, "[trace] %8.3f ms  %s\n", ms, m.first);
+        cudaEventDestroy(m.second);
+    }
+    ctx->trace.clear();
+}
 
 int ws_reserve(dalek_b200_ctx *ctx, DevBuf &b, size_t bytes);
 int pinned_reserve(dalek_b200_ctx *ctx, size_t bytes);
