@@ -61,6 +61,8 @@ def load_library():
     lib.dalek_b200_ristretto_double_and_compress_batch.argtypes = [vp, vp, sz, vp]
     lib.ed25519_b200_verify_each_flat.argtypes = [vp, vp, vp, vp, vp, sz, C.c_int, vp]
     lib.ed25519_b200_verify_each_flat_dev.argtypes = [vp, vp, vp, vp, vp, sz, C.c_int, vp]
+    lib.dalek_b200_scalar_from_wide_batch.argtypes = [vp, vp, sz, vp]
+    lib.dalek_b200_scalar_invert_batch.argtypes = [vp, vp, sz, vp, vp]
     lib.ed25519_b200_last_zs.argtypes = [vp, vp, sz]
     lib.dalek_b200_edwards_mul_base_batch.argtypes = [vp, vp, sz, vp, vp]
     lib.ed25519_b200_sign_batch_flat.argtypes = [vp, vp, vp, vp, sz, vp, vp]
@@ -201,6 +203,20 @@ class Engine:
         out = (C.c_uint8 * 32)()
         rc = self._check(self.lib.dalek_b200_ristretto_vartime_msm(self.h, _ptr(scalars), _ptr(points), n, C.addressof(out)))
         return rc, bytes(out)
+
+    # ---- scalar batches ----
+    def scalar_from_wide_batch(self, wide, n):
+        """Scalar::from_bytes_mod_order_wide for n x 64 B -> n x 32 B."""
+        out = (C.c_uint8 * (32 * max(n, 1)))()
+        self._check(self.lib.dalek_b200_scalar_from_wide_batch(self.h, _ptr(wide), n, C.addressof(out)))
+        return bytes(out)[:32 * n]
+
+    def scalar_invert_batch(self, scalars, n):
+        """Scalar::invert_batch: (inverses n x 32 B, product of all inverses)."""
+        out = (C.c_uint8 * (32 * max(n, 1)))()
+        prod = (C.c_uint8 * 32)()
+        self._check(self.lib.dalek_b200_scalar_invert_batch(self.h, _ptr(scalars), n, C.addressof(out), C.addressof(prod)))
+        return bytes(out)[:32 * n], bytes(prod)
 
     # ---- batch codecs ----
     def decompress_batch(self, encodings, n, ristretto=False):

@@ -170,6 +170,15 @@ int dalek_b200_ristretto_decompress_batch(dalek_b200_ctx *ctx, const uint8_t *in
 int dalek_b200_ristretto_double_and_compress_batch(dalek_b200_ctx *ctx, const uint64_t *limbs, size_t n,
                                                    uint8_t *out);
 
+/* -------- scalar batch helpers ---------------------------------------------
+ * Scalar::from_bytes_mod_order_wide (C/scalar.rs:248-250) for n 64-byte strings -> n canonical 32-byte scalars. */
+int dalek_b200_scalar_from_wide_batch(dalek_b200_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out);
+/* Scalar::invert_batch / invert_batch_alloc (C/scalar.rs:779-853): out[i] = in[i]^-1 mod l (inputs are taken mod l),
+ * out_product = the product of all inverses (the reference's return value; 1 for n = 0).  The reference requires
+ * nonzero inputs (scalar.rs:796-799): a zero input is DALEK_E_INVALID_ARG here. */
+int dalek_b200_scalar_invert_batch(dalek_b200_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out,
+                                   uint8_t out_product[32]);
+
 /* -------- RistrettoPoint ----------------------------------------------------------------- */
 /* n independent RistrettoPoint::multiscalar_mul([a_i, b_i], [G, H]) (constant-time Straus,
  * C/ristretto.rs:964-977 -> C/edwards.rs:970-995 -> straus.rs:103-144), each result compressed

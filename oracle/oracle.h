@@ -71,6 +71,7 @@ void scalar_sub(uint8_t o[32], const uint8_t a[32], const uint8_t b[32]);  /* C/
 void scalar_mul(uint8_t o[32], const uint8_t a[32], const uint8_t b[32]);  /* C/scalar.rs:317-322 */
 void scalar_neg(uint8_t o[32], const uint8_t a[32]);                /* C/scalar.rs:366-374 */
 void scalar_invert(uint8_t o[32], const uint8_t a[32]);             /* C/scalar.rs:739-741 (value only) */
+void scalar_invert_batch(uint8_t *inout, size_t n, uint8_t ret[32]);  /* C/scalar.rs:793-853 (values) */
 void scalar_from_u64(uint8_t o[32], uint64_t x);
 void scalar_non_adjacent_form(int8_t naf[256], const uint8_t a[32], unsigned w); /* C/scalar.rs:955-1007 */
 void scalar_as_radix_16(int8_t out[64], const uint8_t a[32]);       /* C/scalar.rs:1019-1051 */

@@ -6,6 +6,7 @@
  */
 #include "oracle.h"
 #include "constants.h"
+#include <stdlib.h>
 #include <string.h>
 
 typedef unsigned __int128 u128;
@@ -315,4 +316,26 @@ void scalar_as_radix_2w(int8_t digits[64], const uint8_t a[32], unsigned w)
     }
     if (w == 8) digits[digits_count] = (int8_t)(digits[digits_count] + (int8_t)carry);
     else digits[digits_count - 1] = (int8_t)(digits[digits_count - 1] + (int8_t)(carry << w));
+}
+
+/* Scalar::invert_batch_alloc (C/scalar.rs:793-853), values only: every scalar replaced by its inverse mod l,
+ * ret = the product of all inverses.  Inputs must be nonzero (scalar.rs:796-799). */
+void scalar_invert_batch(uint8_t *inout, size_t n, uint8_t ret[32])
+{
+    uint8_t *scratch = (uint8_t *)malloc(32 * (n ? n : 1));
+    uint8_t acc[32], tmp[32];
+    scalar_from_u64(acc, 1);
+    for (size_t i = 0; i < n; i++) {                              /* :819-828 */
+        memcpy(scratch + 32 * i, acc, 32);
+        scalar_reduce(inout + 32 * i, inout + 32 * i);
+        scalar_mul(acc, acc, inout + 32 * i);
+    }
+    scalar_invert(acc, acc);                                      /* :834 */
+    memcpy(ret, acc, 32);                                         /* :837 */
+    for (size_t i = n; i-- > 0;) {                                /* :841-846 */
+        scalar_mul(tmp, acc, inout + 32 * i);
+        scalar_mul(inout + 32 * i, acc, scratch + 32 * i);
+        memcpy(acc, tmp, 32);
+    }
+    free(scratch);
 }

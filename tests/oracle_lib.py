@@ -157,6 +157,15 @@ class Oracle:
             raise ValueError("more static scalars than static points")
         return o if rc else None
 
+    def scalar_invert_batch(self, scalars):
+        """Scalar::invert_batch (C/scalar.rs:779-853): (list of inverses, product of all inverses)."""
+        n = len(scalars)
+        b = (C.c_uint8 * (32 * max(n, 1))).from_buffer_copy(b"".join(scalars) + bytes(32 * (1 if n == 0 else 0)))
+        ret = (C.c_uint8 * 32)()
+        self.lib.scalar_invert_batch(b, C.c_size_t(n), ret)
+        raw = bytes(b)
+        return [raw[32 * i:32 * i + 32] for i in range(n)], bytes(ret)
+
     def compress_batch(self, points):
         """EdwardsPoint::compress_batch (C/edwards.rs:619-647)."""
         arr, _ = self._pts(points)

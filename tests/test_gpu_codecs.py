@@ -114,3 +114,23 @@ def test_codecs_large_round_trip(eng, oracle):
     for i in (0, 65535, 65536, n - 1):
         q = oracle.scalarmul(t[i].tobytes(), oracle.basepoint())
         assert dbl[32 * i:32 * i + 32] == oracle.ristretto_compress(oracle.double(q))
+
+
+def test_scalar_batches(eng, oracle):
+    """Scalar::from_bytes_mod_order_wide and Scalar::invert_batch (SURVEY 8f rank 4) against the oracle / big integers."""
+    import curve25519_dalek_b200 as pkg
+    rnd = random.Random(12)
+    wide = [rnd.randbytes(64) for _ in range(300)] + [bytes(64), b"\xff" * 64, pyref.L.to_bytes(64, "little")]
+    got = eng.scalar_from_wide_batch(b"".join(wide), len(wide))
+    assert [int.from_bytes(got[32 * i:32 * i + 32], "little") for i in range(len(wide))] == [int.from_bytes(w, "little") % pyref.L for w in wide]
+    for n in (0, 1, 7, 8, 9, 1000):
+        xs = [rnd.randrange(1, 2**255) for _ in range(n)]
+        xs = [x if x % pyref.L else 1 for x in xs]
+        if n >= 9:
+            xs[0], xs[1], xs[8] = 1, pyref.L - 1, pyref.L + 5
+        inv, prod = eng.scalar_invert_batch(b"".join(b32(x) for x in xs), n)
+        want_inv, want_prod = oracle.scalar_invert_batch([b32(x) for x in xs])
+        assert inv == b"".join(want_inv) and prod == want_prod
+        assert all(int.from_bytes(inv[32 * i:32 * i + 32], "little") * xs[i] % pyref.L == 1 for i in range(n))
+    with pytest.raises(pkg.EngineError):                      # a zero input violates the precondition
+        eng.scalar_invert_batch(b"".join(b32(x) for x in (5, pyref.L, 7)), 3)

@@ -346,3 +346,16 @@ def test_precomputed_straus_and_batch_codecs(oracle, kat):
     small = [oracle.ristretto_decompress(e) for e in encs[:8]]
     got = oracle.ristretto_double_and_compress_batch(small)
     assert [got[32 * i:32 * i + 32] for i in range(8)] == [encs[2 * i] for i in range(8)]
+
+
+def test_scalar_invert_batch(oracle):
+    """Scalar::invert_batch against the doc example of C/scalar.rs:765-778 (3, 5, 7, 11) and big-integer inverses."""
+    b32 = lambda x: x.to_bytes(32, "little")
+    xs = [3, 5, 7, 11, pyref.L - 1, 2**255 - 1, 1]
+    inv, prod = oracle.scalar_invert_batch([b32(x) for x in xs])
+    assert [int.from_bytes(v, "little") for v in inv] == [pow(x % pyref.L, -1, pyref.L) for x in xs]
+    want = 1
+    for x in xs:
+        want = want * pow(x % pyref.L, -1, pyref.L) % pyref.L
+    assert int.from_bytes(prod, "little") == want
+    assert oracle.scalar_invert_batch([])[1] == b32(1)
