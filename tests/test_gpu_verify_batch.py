@@ -315,3 +315,23 @@ def test_verify_batches_large_device(eng, oracle):
     assert rc == VERIFY and v == [VERIFY if k in (0, 100) else OK for k in range(n // bs)]
     # the option set for the call is restored afterwards
     assert eng.verify_batch_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, device_ptrs=True) == VERIFY
+
+
+def test_verify_batches_all_distinct_keys_with_failure(eng, oracle):
+    """Every key different (no merging possible) and one bad batch: the bisection evaluates sub-ranges through the
+    per-key accumulation path; exactly that batch must fail, with and without key merging."""
+    msgs, sigs, pks = make_batch(oracle, 100, seed=4321)
+    bs, nb = 16, 7
+    flat, offs = _flat(msgs)
+    for dedupe in (1, 0):
+        eng.set_option("dedupe_keys", dedupe)
+        try:
+            rc, v = eng.verify_batches_flat(flat, offs, b"".join(sigs), b"".join(pks), 100, bs)
+            assert rc == OK and v == [OK] * nb
+            bad = list(sigs); x = bytearray(bad[16 * 4 + 9]); x[33] ^= 8; bad[16 * 4 + 9] = bytes(x)
+            rc, v = eng.verify_batches_flat(flat, offs, b"".join(bad), b"".join(pks), 100, bs)
+            assert rc == VERIFY and v == [VERIFY if k == 4 else OK for k in range(nb)]
+            want = [oracle.verify_batch(msgs[k * bs:(k + 1) * bs], bad[k * bs:(k + 1) * bs], pks[k * bs:(k + 1) * bs]) for k in range(nb)]
+            assert v == want
+        finally:
+            eng.set_option("dedupe_keys", 1)
