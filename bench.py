@@ -167,14 +167,6 @@ class MsmWorkload:
         assert rc == 0
         return comp
 
-    def step_partial(self, host):
-        s = self.h_scalars if host else self.d_scalars
-        p = self.h_points if host else self.d_points
-        rc, win = self.eng.edwards_msm_partial(s.data_ptr(), p.data_ptr(), self.n, self.n_total, point_fmt=1,
-                                               device_ptrs=not host)
-        assert rc == 0
-        return win
-
 
 def run_msm(args, rank, world, local):
     import numpy as np
@@ -184,24 +176,25 @@ def run_msm(args, rank, world, local):
 
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("DALEK_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))      # NCCL_DEBUG is left to the caller
     eng = pkg.Engine(local)
     n_local = args.pairs_per_gpu or ((1 << 20) if world == 1 else (1 << 21))
     n_total = n_local * world
     wl = MsmWorkload(eng, n_local, n_total, rank, torch)
-    nwin = eng.msm_window_count(n_total)
     dev = torch.device("cuda", local)
+    # N > 1: the shard's MSM, the NCCL all-gather of the window-accumulator records and the combine are all enqueued
+    # on the engine's stream (curve25519_dalek_b200/sharding.py); the window width comes from the shard size
+    from curve25519_dalek_b200.sharding import ShardedMsm
+    sharded = ShardedMsm(eng, world, n_local, dev) if world > 1 else None
+    nwin = eng.msm_window_count(n_local)
 
     def step(host=False):
         if world == 1:
             return wl.step_host_single() if host else wl.step_device_single()
-        win = wl.step_partial(host)
-        mine = torch.frombuffer(bytearray(bytes(win)), dtype=torch.int64).to(dev)
-        gathered = torch.empty(world * nwin * 20, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(gathered, mine)          # the one exchange step of the sharded MSM
-        allw = gathered.cpu().numpy().view(np.uint64)
-        comp, _ = eng.edwards_msm_combine(allw, world, n_total)
+        s = wl.h_scalars if host else wl.d_scalars
+        p = wl.h_points if host else wl.d_points
+        rc, comp = sharded.run(s.data_ptr(), p.data_ptr(), n_local, 1, not host)
+        assert rc == 0
         return comp
 
     def barrier():
@@ -269,7 +262,7 @@ def run_msm(args, rank, world, local):
         kms = statistics.mean(kernel_ms)
         algo_bytes = n_local * 192
         achieved = algo_bytes / (kms * 1e-3) / 1e9
-        c = eng_window_bits(n_total)
+        c = eng_window_bits(n_local)          # chosen from the shard size (the work one GPU does)
         adds = n_local * ((253 + c - 1) // c)
         field_muls = adds * 8                # 8M per projective-Niels addition (curve_models.rs:411-430 + :365-372)
         traffic = None
@@ -288,9 +281,11 @@ def run_msm(args, rank, world, local):
                        "timing": "value / ms_per_step: K blocking C-ABI calls bracketed by barrier + device sync, max over ranks; "
                                  "device_ms_per_step: CUDA events on the engine's stream around each call (rank 0)",
                        "device_ms_per_step": statistics.mean(call_ms), "e2e_device_ms_per_step": statistics.mean(e2e_call_ms),
-                       "parity": "algebraic identity sum s_i(t_i B) == (sum s_i t_i)B checked at full size"},
+                       "parity": "algebraic identity sum s_i(t_i B) == (sum s_i t_i)B checked at full size",
+                       "exchange": None if world == 1 else "one NCCL all-gather of %d-byte records (window accumulators) per rank, enqueued on "
+                                   "the engine's stream between the shard MSM and the combine; no host bounce" % sharded.rec_bytes},
             "e2e": {"value": n_total * args.steps / e2e_t, "unit": "points/s",
-                    "h2d_bytes_per_step": n_local * 192, "d2h_bytes_per_step": 192 if world == 1 else nwin * 160 + 192},
+                    "h2d_bytes_per_step": n_local * 192, "d2h_bytes_per_step": 192},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_bucket_accumulate", "achieved": achieved, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
@@ -307,6 +302,26 @@ def run_msm(args, rank, world, local):
             "clocks": clocks,
         }
     return line, eng, wl
+
+
+def run_msm_like_for_like(eng, n, steps):
+    """The N = 1 rate at the per-GPU size of the N > 1 runs (2^21 pairs): the like-for-like denominator of the scaling
+    efficiency.  Device-resident, same call as the headline."""
+    import torch
+    wl = MsmWorkload(eng, n, n, 7, torch)
+    for _ in range(3):
+        wl.step_device_single()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    kms = []
+    for _ in range(steps):
+        wl.step_device_single()
+        kms.append(eng.last_kernel_ms()[0])
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    return {"metric": "Pippenger MSM points/sec, 2^21 pairs on one GPU (the shard size of the N > 1 runs)", "value": n / dt,
+            "unit": "points/s", "ms_per_step": dt * 1e3, "pairs": n, "window_bits": eng_window_bits(n),
+            "bucket_kernel_ms": statistics.mean(kms)}
 
 
 def eng_window_bits(n):
@@ -348,7 +363,6 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
     warmup = args.warmup if warmup is None else warmup
     torch.cuda.set_device(local)
     if world > 1 and not dist.is_initialized():
-        os.environ["NCCL_DEBUG"] = os.environ.get("DALEK_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = eng or pkg.Engine(local)
     n = args.sigs_per_gpu or (1 << 22)
@@ -537,91 +551,161 @@ def run_double_base(eng, n=1 << 20, steps=3):
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline (oracle)
-def cpu_msm_baseline(n, threads):
-    """Oracle Pippenger (reference algorithm, w = 8) on `n` pairs split over `threads` host threads."""
-    import numpy as np
-    import oracle_lib
-    orc = oracle_lib.load()
-    lib = orc.lib
-    pts = np.empty((n, 20), dtype=np.uint64)
-    t0b = (0x1234567 + SEED).to_bytes(32, "little")
-    qb = (0x9e3779b97f4a7c15f39cc0605cedc834 % L_ORDER).to_bytes(32, "little")
-    lib.oracle_points_progression(pts.ctypes.data_as(C.c_void_p), C.c_size_t(n), t0b, qb)
-    sc = fast_scalars(n, seed=77)
-    outs = np.zeros((threads, 20), dtype=np.uint64)
-    bounds = [n * i // threads for i in range(threads + 1)]
+def physical_cores():
+    """Distinct (package, core) pairs of /proc/cpuinfo; None if it cannot be read."""
+    try:
+        seen, phys, core = set(), None, None
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("physical id"):
+                phys = ln.split(":")[1].strip()
+            elif ln.startswith("core id"):
+                core = ln.split(":")[1].strip()
+            elif not ln.strip():
+                if phys is not None and core is not None:
+                    seen.add((phys, core))
+                phys = core = None
+        return len(seen) or None
+    except OSError:
+        return None
 
-    def work(i):
-        lo, hi = bounds[i], bounds[i + 1]
-        lib.oracle_msm_limbs(outs[i].ctypes.data_as(C.c_void_p), sc[lo:hi].ctypes.data_as(C.c_void_p),
-                             pts[lo:hi].ctypes.data_as(C.c_void_p), C.c_size_t(hi - lo))
-    t0 = time.perf_counter()
-    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
-    [t.start() for t in ths]
-    [t.join() for t in ths]
-    res = (C.c_uint8 * 32)()
-    lib.oracle_sum_points(res, None, outs.ctypes.data_as(C.c_void_p), C.c_size_t(threads))
-    dt = time.perf_counter() - t0
+
+class CpuPool:
+    """Persistent worker threads of the oracle (oracle/parallel.c): every thread runs the unmodified, single-threaded
+    reference restatement on an independent slice.  Checker / baseline infrastructure only."""
+
+    def __init__(self, threads):
+        import oracle_lib
+        self.orc = oracle_lib.load()
+        lib = self.lib = self.orc.lib
+        vp, sz, dbl = C.c_void_p, C.c_size_t, C.c_double
+        lib.oracle_pool_create.restype = vp; lib.oracle_pool_create.argtypes = [C.c_int]
+        lib.oracle_pool_destroy.argtypes = [vp]
+        lib.oracle_pool_msm.restype = dbl; lib.oracle_pool_msm.argtypes = [vp, vp, vp, vp, sz, sz]
+        lib.oracle_pool_verify_batches.restype = dbl; lib.oracle_pool_verify_batches.argtypes = [vp, vp, sz, vp, vp, sz, sz, vp]
+        lib.oracle_pool_verify_each.restype = dbl; lib.oracle_pool_verify_each.argtypes = [vp, vp, sz, vp, vp, sz, C.c_int, vp]
+        lib.oracle_pool_double_base.restype = dbl; lib.oracle_pool_double_base.argtypes = [vp, vp, vp, vp, vp, vp, sz, vp]
+        self.threads = threads
+        self.h = lib.oracle_pool_create(threads)
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_pool_destroy(self.h)
+            self.h = None
+
+    def msm_inputs(self, n):
+        import numpy as np
+        pts = np.empty((n, 20), dtype=np.uint64)
+        t0b = (0x1234567 + SEED).to_bytes(32, "little")
+        qb = (0x9e3779b97f4a7c15f39cc0605cedc834 % L_ORDER).to_bytes(32, "little")
+        self.lib.oracle_points_progression(pts.ctypes.data_as(C.c_void_p), C.c_size_t(n), t0b, qb)
+        return fast_scalars(n, seed=77), pts
+
+    def msm(self, sc, pts, n, slice_pairs=8192):
+        """One n-pair MSM as independent reference Pippenger sub-MSMs (w = 8, pippenger.rs:81-87) of `slice_pairs` pairs
+        pulled by the pool's threads; partial sums added.  Returns seconds."""
+        out = (C.c_uint8 * 32)()
+        return self.lib.oracle_pool_msm(self.h, C.addressof(out), sc.ctypes.data, pts.ctypes.data, n, slice_pairs), bytes(out)
+
+    def verify_inputs(self, nsigs, nkeys=64):
+        import numpy as np
+        orc = self.orc
+        seeds = [hashlib.sha512(b"dalek-b200/sk" + k.to_bytes(8, "little")).digest()[:32] for k in range(nkeys)]
+        pk = [orc.public_key(s) for s in seeds]
+        base = 256                                          # sign 256 distinct messages, tile them (the CPU cost does not depend on repeats)
+        msgs = [b"a" * 51 + i.to_bytes(8, "little") for i in range(base)]
+        sigs = [orc.sign(m, seeds[i % nkeys]) for i, m in enumerate(msgs)]
+        reps = (nsigs + base - 1) // base
+        m = np.frombuffer(b"".join(msgs) * reps, dtype=np.uint8)[:59 * nsigs].copy()
+        s = np.frombuffer(b"".join(sigs) * reps, dtype=np.uint8)[:64 * nsigs].copy()
+        k = np.frombuffer(b"".join(pk[i % nkeys] for i in range(base)) * reps, dtype=np.uint8)[:32 * nsigs].copy()
+        return m, s, k
+
+    def verify_batches(self, m, s, k, nsigs, batch=256):
+        import numpy as np
+        verd = np.zeros((nsigs + batch - 1) // batch, dtype=np.int32)
+        dt = self.lib.oracle_pool_verify_batches(self.h, m.ctypes.data, 59, s.ctypes.data, k.ctypes.data, nsigs, batch, verd.ctypes.data)
+        assert not verd.any(), "oracle rejected valid signatures"
+        return dt
+
+    def verify_each(self, m, s, k, nsigs):
+        import numpy as np
+        res = np.zeros(nsigs, dtype=np.uint8)
+        dt = self.lib.oracle_pool_verify_each(self.h, m.ctypes.data, 59, s.ctypes.data, k.ctypes.data, nsigs, 0, res.ctypes.data)
+        assert not res.any(), "oracle rejected valid signatures"
+        return dt
+
+    def double_base(self, a, b, G, H, n):
+        import numpy as np
+        out = np.zeros((n, 32), dtype=np.uint8)
+        ok = C.c_int(0)
+        dt = self.lib.oracle_pool_double_base(self.h, out.ctypes.data, a.ctypes.data, b.ctypes.data, G, H, n, C.byref(ok))
+        assert ok.value == 1
+        return dt, out
+
+
+def cpu_msm_baseline(n, threads):
+    """Oracle Pippenger (reference algorithm) on `n` pairs over `threads` persistent host threads: (points/s, seconds)."""
+    pool = CpuPool(threads)
+    sc, pts = pool.msm_inputs(n)
+    dt, _ = pool.msm(sc, pts, n, slice_pairs=n if threads == 1 else 8192)
+    pool.close()
     return n / dt, dt
 
 
 def cpu_verify_baseline(nsigs, threads, batch=256):
-    import oracle_lib
-    orc = oracle_lib.load()
-    msgs = [b"a" * 51 + i.to_bytes(8, "little") for i in range(batch)]
-    seeds = [hashlib.sha512(b"dalek-b200/sk" + k.to_bytes(8, "little")).digest()[:32] for k in range(batch)]
-    pks = [orc.public_key(s) for s in seeds]
-    sigs = [orc.sign(m, s) for m, s in zip(msgs, seeds)]
-    reps = max(1, nsigs // (batch * threads))
-    ok = []
-
-    def work():
-        for _ in range(reps):
-            ok.append(orc.verify_batch(msgs, sigs, pks))
-    t0 = time.perf_counter()
-    ths = [threading.Thread(target=work) for _ in range(threads)]
-    [t.start() for t in ths]
-    [t.join() for t in ths]
-    dt = time.perf_counter() - t0
-    assert all(r == 0 for r in ok)
-    return reps * threads * batch / dt, dt
+    pool = CpuPool(threads)
+    m, s, k = pool.verify_inputs(nsigs)
+    dt = pool.verify_batches(m, s, k, nsigs, batch)
+    pool.close()
+    return nsigs / dt, dt
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the CPU oracle (C restatement of the reference's serial u64 backend; the Rust reference cannot
+    be built in this image) on ALL host threads, same metric and -- for the MSM -- the same configuration as the GPU arm
+    at N = 1 (2^20 pairs per step), persistent worker threads, sub-MSMs of 2^13 pairs."""
     if rank != 0:
         return None
     threads = os.cpu_count() or 1
     steps = max(1, args.steps)
+    pool = CpuPool(threads)
+    vals = []
     if args.workload == "verify":
-        vals = []
-        for _ in range(args.warmup and 1):
-            cpu_verify_baseline(256 * threads, threads)
+        nsigs = 256 * threads * 4
+        m, s, k = pool.verify_inputs(nsigs)
+        for _ in range(min(args.warmup, 1)):
+            pool.verify_batches(m, s, k, nsigs)
         t0 = time.perf_counter()
         for _ in range(steps):
-            v, dt = cpu_verify_baseline(256 * threads * 4, threads)
-            vals.append(v)
+            vals.append(nsigs / pool.verify_batches(m, s, k, nsigs))
         el = time.perf_counter() - t0
-        val = statistics.mean(vals)
-        metric, unit, sample = "Ed25519 verify_batch signatures/sec", "sigs/s", "each step: %d threads x 4 batches of 256 signatures (reference's largest published batch size)" % threads
-        config = {"workload": "ed25519_verify_batch", "batch": 256}
+        metric, unit = "Ed25519 verify_batch signatures/sec", "sigs/s"
+        sample = "each step: %d independent verify_batch calls of 256 signatures (the reference's largest published batch size) pulled by %d persistent threads" % (nsigs // 256, threads)
+        config = {"workload": "ed25519_verify_batch", "batch": 256, "signatures_per_step": nsigs}
+        same = False
     else:
-        n = 1 << 17
-        vals = []
-        for _ in range(args.warmup and 1):
-            cpu_msm_baseline(1 << 14, threads)
+        n_total = (args.pairs_per_gpu or ((1 << 20) if world == 1 else (1 << 21))) * world      # the GPU arm's configuration
+        n = min(n_total, 1 << 22)                           # bounded sample per step (the rate does not depend on n beyond 2^13-pair slices)
+        sc, pts = pool.msm_inputs(n)
+        for _ in range(min(args.warmup, 1)):
+            pool.msm(sc, pts, n)
         t0 = time.perf_counter()
         for _ in range(steps):
-            v, dt = cpu_msm_baseline(n, threads)
-            vals.append(v)
+            vals.append(n / pool.msm(sc, pts, n)[0])
         el = time.perf_counter() - t0
-        val = statistics.mean(vals)
         metric, unit = "Pippenger MSM points/sec", "points/s"
-        sample = "each step: one 2^17-pair MSM (reference Pippenger, w=8) split into %d independent sub-MSMs, one per host thread, partial sums added" % threads
-        config = {"workload": "pippenger_msm", "pairs_total": n, "point_format": "extended radix-2^51 limbs (160 B)"}
+        sample = ("each step: one 2^%d-pair MSM (the GPU arm's configuration%s) as %d independent reference Pippenger sub-MSMs of 8192 pairs "
+                  "(w = 8) pulled by %d persistent threads, partial sums added" % (n.bit_length() - 1, "" if n == n_total else ", capped at 2^22 pairs per step", (n + 8191) // 8192, threads))
+        config = {"workload": "pippenger_msm", "pairs_total": n_total, "pairs_per_gpu": n_total // world, "pairs_per_step_sampled": n,
+                  "point_format": "extended radix-2^51 limbs (160 B)"}
+        same = n == n_total
+    pool.close()
+    val = statistics.mean(vals)
     return {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": world, "steps": steps,
             "warmup": args.warmup, "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 limbs (radix 2^51), exact", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": val, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+            "same_config_as_gpu_arm": same,
+            "cpu_baseline": {"value": val, "unit": unit, "cores": threads, "physical_cores": physical_cores(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU oracle = C restatement of the reference's serial u64 backend (Rust toolchain absent: oracle/_ref cannot be built)"}
 
@@ -655,7 +739,13 @@ def main():
         line = run_verify(args, rank, world, local)
     else:
         line, eng, wl = run_msm(args, rank, world, local)
+        if not args.no_extras and world > 1:
+            # BASELINE.json's metric names verify_batch at 1/2/4/8 GPUs too: independent replicas, one batch per GPU
+            v = run_verify(args, rank, world, local, eng=eng, steps=min(args.steps, 5), warmup=3)
+            if rank == 0:
+                line["verify_batch"] = {k: v[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "e2e", "config", "gpu_launches", "roofline")}
         if not args.no_extras and world == 1:
+            line["msm_2p21_pairs"] = run_msm_like_for_like(eng, 1 << 21, min(args.steps, 20))
             line["msm_precomputed"] = run_precomputed(eng, wl)
             line["codecs"] = run_codecs(eng, wl)
             v = run_verify(args, rank, world, local, eng=eng, steps=min(args.steps, 5), warmup=3)

@@ -77,7 +77,7 @@ int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value)
     if (!strcmp(name, "dedupe_keys")) { ctx->opt_dedupe_keys = value ? 1 : 0; return 0; }
     if (!strcmp(name, "verify_pieces")) { if (value < 1 || value > 8) return DALEK_E_INVALID_ARG; ctx->opt_verify_pieces = value; return 0; }
     if (!strcmp(name, "field_f64")) { ctx->opt_field_f64 = value ? 1 : 0; return 0; }
-    if (!strcmp(name, "verify_chunk")) { if (value < 1 || value > (1 << 20)) return DALEK_E_INVALID_ARG; ctx->opt_verify_chunk = value; return 0; }
+    if (!strcmp(name, "verify_chunk")) { if (value < 0 || value > (1 << 20)) return DALEK_E_INVALID_ARG; ctx->opt_verify_chunk = value; return 0; }
     return DALEK_E_INVALID_ARG;
 }
 
@@ -108,7 +108,8 @@ static size_t point_in_bytes(int fmt) { return fmt == DALEK_POINTS_COMPRESSED ? 
 // Host inputs are streamed in chunks on a dedicated copy stream: while chunk k+1 crosses PCIe,
 // chunk k is converted, sorted and added into the (persistent) bucket sums.
 static int run_msm(dalek_b200_ctx *ctx, const void *scalars, const void *points_in, bool on_device, int point_fmt, size_t n,
-                   size_t n_total, ge_p3_raw *d_windows, int *bad_out, MsmResult *d_result)
+                   size_t n_window /* the size the window width is chosen from: n, or the shard size of a sharded MSM */,
+                   ge_p3_raw *d_windows, int *bad_out, MsmResult *d_result)
 {
     int rc;
     const int kind = point_fmt == DALEK_POINTS_COMPRESSED ? PK_NIELS : PK_PNIELS;
@@ -118,7 +119,7 @@ static int run_msm(dalek_b200_ctx *ctx, const void *scalars, const void *points_
     if ((rc = ws_reserve(ctx, ctx->points, std::max<size_t>(1, n) * psz))) return rc;
     if ((rc = ws_reserve(ctx, ctx->flags, 64))) return rc;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->flags.p, 0, 64, st));
-    const int c = msm_choose_window_bits(ctx, n_total);
+    const int c = msm_choose_window_bits(ctx, n_window);
     if (on_device) {
         if ((rc = msm_prepare_points(ctx, points_in, point_fmt, n, ctx->points.p, (int *)ctx->flags.p))) return rc;
         if ((rc = msm_accumulate_chunk(ctx, (const uint32_t *)scalars, ctx->points.p, kind, n, c, true))) return rc;
@@ -204,90 +205,190 @@ int dalek_b200_edwards_vartime_msm_dev(dalek_b200_ctx *ctx, const void *d_scalar
     return msm_common(ctx, d_scalars, d_points, true, point_fmt, n, out_compressed, out_limbs);
 }
 
-int dalek_b200_msm_window_count(dalek_b200_ctx *ctx, size_t n_total)
+int dalek_b200_msm_window_count(dalek_b200_ctx *ctx, size_t n_shard)
 {
     if (!ctx) return DALEK_E_INVALID_ARG;
-    return msm_window_count_for_bits(msm_choose_window_bits(ctx, n_total));
+    return msm_window_count_for_bits(msm_choose_window_bits(ctx, n_shard));
 }
 
-static int partial_common(dalek_b200_ctx *ctx, const void *scalars, const void *points, bool on_device, int point_fmt,
-                          size_t n_local, size_t n_total, uint64_t *out_windows);
-
-int dalek_b200_edwards_msm_partial(dalek_b200_ctx *ctx, const uint8_t *scalars, const void *points, int point_fmt,
-                                   size_t n_local, size_t n_total, uint64_t *out_windows)
+size_t dalek_b200_msm_partial_bytes(dalek_b200_ctx *ctx, size_t n_shard)
 {
-    return partial_common(ctx, scalars, points, false, point_fmt, n_local, n_total, out_windows);
+    if (!ctx) return 0;
+    return (size_t)msm_window_count_for_bits(msm_choose_window_bits(ctx, n_shard)) * 160 + 8;
 }
 
-int dalek_b200_edwards_msm_partial_dev(dalek_b200_ctx *ctx, const void *d_scalars, const void *d_points, int point_fmt,
-                                       size_t n_local, size_t n_total, uint64_t *out_windows)
-{
-    return partial_common(ctx, d_scalars, d_points, true, point_fmt, n_local, n_total, out_windows);
-}
+void *dalek_b200_stream(dalek_b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 }  // extern "C"
 
-// window accumulators cross the boundary as canonical radix-2^51 limbs (20 u64 each)
-__global__ void k_windows_to_limbs(const ge_p3_raw *__restrict__ win, int nwin, uint64_t *__restrict__ out)
+// A shard's record as it crosses the boundary (and the exchange between ranks): the window accumulators as
+// canonical radix-2^51 limbs (20 u64 each, window 0 = least significant) followed by one u64 status word
+// (non-zero: a compressed point of the shard did not decode).
+__global__ void k_windows_to_record(const ge_p3_raw *__restrict__ win, int nwin, const int *__restrict__ bad, uint64_t *__restrict__ out)
 {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w == nwin) out[20 * (size_t)nwin] = (uint64_t)(*bad != 0);
     if (w >= nwin) return;
     ge_p3 p; ge_p3_raw r = win[w]; ge_p3_load_raw(p, r);
     fe_to_limbs51(out + 20 * w, p.X); fe_to_limbs51(out + 20 * w + 5, p.Y);
     fe_to_limbs51(out + 20 * w + 10, p.Z); fe_to_limbs51(out + 20 * w + 15, p.T);
 }
-__global__ void k_limbs_to_windows(const uint64_t *__restrict__ in, int count, ge_p3_raw *__restrict__ win)
+// `ranks` records of `rec_words` u64 each -> ranks x nwin raw accumulators; *any_bad |= status words
+__global__ void k_records_to_windows(const uint64_t *__restrict__ in, int ranks, int nwin, size_t rec_words,
+                                     ge_p3_raw *__restrict__ win, int *__restrict__ any_bad)
 {
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= count) return;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ranks * nwin) return;
+    const int r = t / nwin, w = t % nwin;
+    const uint64_t *src = in + (size_t)r * rec_words + 20 * (size_t)w;
     ge_p3 p;
-    fe_from_limbs51(p.X, in + 20 * w); fe_from_limbs51(p.Y, in + 20 * w + 5);
-    fe_from_limbs51(p.Z, in + 20 * w + 10); fe_from_limbs51(p.T, in + 20 * w + 15);
-    ge_p3_raw r; ge_p3_store_raw(r, p); win[w] = r;
+    fe_from_limbs51(p.X, src); fe_from_limbs51(p.Y, src + 5); fe_from_limbs51(p.Z, src + 10); fe_from_limbs51(p.T, src + 15);
+    ge_p3_raw o; ge_p3_store_raw(o, p); win[t] = o;
+    if (w == 0 && rec_words > 20 * (size_t)nwin && in[(size_t)r * rec_words + 20 * (size_t)nwin]) atomicOr(any_bad, 1);
 }
 
-static int partial_common(dalek_b200_ctx *ctx, const void *scalars, const void *points, bool on_device, int point_fmt,
-                          size_t n_local, size_t n_total, uint64_t *out_windows)
+// Enqueue the partial MSM of one shard on the context's stream and leave its record (window accumulators +
+// status word) in ctx->misc1; nothing is synchronised.  ev_a .. ev_b bracket the bucket accumulation.
+static int partial_enqueue(dalek_b200_ctx *ctx, const void *scalars, const void *points, bool on_device, int point_fmt,
+                           size_t n_local, size_t n_shard, int *nwin_out)
 {
-    if (!ctx || !out_windows || (n_local && (!scalars || !points)) || n_local > n_total ||
+    if (!ctx || (n_local && (!scalars || !points)) || n_local > n_shard ||
         (point_fmt != DALEK_POINTS_COMPRESSED && point_fmt != DALEK_POINTS_EXTENDED) || n_local >= (1ull << 31))
         return DALEK_E_INVALID_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    CallTimer timer(ctx);
     int rc;
-    int c = msm_choose_window_bits(ctx, n_total);
-    int nwin = msm_window_count_for_bits(c);
+    const int c = msm_choose_window_bits(ctx, n_shard);
+    const int nwin = msm_window_count_for_bits(c);
     if ((rc = ws_reserve(ctx, ctx->misc0, (size_t)nwin * sizeof(ge_p3_raw)))) return rc;
-    if ((rc = ws_reserve(ctx, ctx->misc1, (size_t)nwin * 160))) return rc;
-    if ((rc = pinned_reserve(ctx, (size_t)nwin * 160 + 64))) return rc;
-    int *h_bad = (int *)((char *)ctx->h_pinned + (size_t)nwin * 160);
-    *h_bad = 0;
-    if ((rc = run_msm(ctx, scalars, points, on_device, point_fmt, n_local, n_total, (ge_p3_raw *)ctx->misc0.p, h_bad, nullptr))) return rc;
-    k_windows_to_limbs<<<(nwin + 63) / 64, 64, 0, ctx->stream>>>((const ge_p3_raw *)ctx->misc0.p, nwin, (uint64_t *)ctx->misc1.p);
+    if ((rc = ws_reserve(ctx, ctx->misc1, (size_t)nwin * 160 + 8))) return rc;
+    if ((rc = run_msm(ctx, scalars, points, on_device, point_fmt, n_local, n_shard, (ge_p3_raw *)ctx->misc0.p, nullptr, nullptr))) return rc;
+    k_windows_to_record<<<(nwin + 1 + 63) / 64, 64, 0, ctx->stream>>>((const ge_p3_raw *)ctx->misc0.p, nwin, (const int *)ctx->flags.p,
+                                                                     (uint64_t *)ctx->misc1.p);
     ctx->launches++;
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->misc1.p, (size_t)nwin * 160, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    *nwin_out = nwin;
+    return 0;
+}
+
+static void read_kernel_ms(dalek_b200_ctx *ctx)
+{
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
+}
+
+static int partial_common(dalek_b200_ctx *ctx, const void *scalars, const void *points, bool on_device, int point_fmt,
+                          size_t n_local, size_t n_shard, uint64_t *out_windows)
+{
+    if (!ctx || !out_windows) return DALEK_E_INVALID_ARG;
+    CallTimer timer(ctx);
+    int rc, nwin = 0;
+    if ((rc = partial_enqueue(ctx, scalars, points, on_device, point_fmt, n_local, n_shard, &nwin))) return rc;
+    const size_t bytes = (size_t)nwin * 160 + 8;
+    if ((rc = pinned_reserve(ctx, bytes))) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->misc1.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    read_kernel_ms(ctx);
     memcpy(out_windows, ctx->h_pinned, (size_t)nwin * 160);
+    uint64_t status; memcpy(&status, (const char *)ctx->h_pinned + (size_t)nwin * 160, 8);
+    return status ? DALEK_NONE : DALEK_OK;
+}
+
+static int partial_async_common(dalek_b200_ctx *ctx, const void *scalars, const void *points, bool on_device, int point_fmt,
+                                size_t n_local, size_t n_shard, void *d_out_record)
+{
+    if (!ctx || !d_out_record) return DALEK_E_INVALID_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_call0, ctx->stream));     // the device span ends in ..._combine_dev
+    ctx->async_open = true;
+    int rc, nwin = 0;
+    if ((rc = partial_enqueue(ctx, scalars, points, on_device, point_fmt, n_local, n_shard, &nwin))) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_out_record, ctx->misc1.p, (size_t)nwin * 160 + 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    return DALEK_OK;
+}
+
+// records (host or device) -> Horner over windows -> result read-back
+static int combine_common(dalek_b200_ctx *ctx, const void *records, bool on_device, size_t rec_bytes, int ranks, size_t n_shard,
+                          uint8_t out_compressed[32], uint64_t out_limbs[20])
+{
+    if (!ctx || !records || ranks < 1 || ranks > 1024) return DALEK_E_INVALID_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    const int c = msm_choose_window_bits(ctx, n_shard);
+    const int nwin = msm_window_count_for_bits(c);
+    const size_t cnt = (size_t)ranks * nwin;
+    if ((rc = ws_reserve(ctx, ctx->red_c, cnt * sizeof(ge_p3_raw)))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->flags, 64))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->result, sizeof(MsmResult)))) return rc;
+    if ((rc = pinned_reserve(ctx, sizeof(MsmResult) + 64))) return rc;
+    cudaStream_t st = ctx->stream;
+    const void *d_rec = records;
+    if (!on_device) {
+        if ((rc = ws_reserve(ctx, ctx->red_d, (size_t)ranks * rec_bytes))) return rc;
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->red_d.p, records, (size_t)ranks * rec_bytes, cudaMemcpyHostToDevice, st));
+        d_rec = ctx->red_d.p;
+    }
+    int *d_bad = (int *)ctx->flags.p + 8;                       // flags[0] belongs to a partial call still in flight
+    CUDA_TRY(ctx, cudaMemsetAsync(d_bad, 0, 4, st));
+    k_records_to_windows<<<(unsigned)((cnt + 63) / 64), 64, 0, st>>>((const uint64_t *)d_rec, ranks, nwin, rec_bytes / 8,
+                                                                      (ge_p3_raw *)ctx->red_c.p, d_bad);
+    ctx->launches++;
+    if ((rc = msm_combine_windows(ctx, (const ge_p3_raw *)ctx->red_c.p, ranks, nwin, c, (MsmResult *)ctx->result.p))) return rc;
+    MsmResult *h = (MsmResult *)ctx->h_pinned;
+    int *h_bad = (int *)((char *)ctx->h_pinned + sizeof(MsmResult));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->result.p, sizeof(MsmResult), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+    if (ctx->async_open) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_call1, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (ctx->async_open) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_call0, ctx->ev_call1) == cudaSuccess) ctx->last_call_ms = ms;
+        read_kernel_ms(ctx);                                     // the bucket kernels of the partial call
+        ctx->async_open = false;
+    }
+    if (out_compressed) memcpy(out_compressed, h->compressed, 32);
+    if (out_limbs) memcpy(out_limbs, h->limbs, 160);
     return *h_bad ? DALEK_NONE : DALEK_OK;
 }
 
-extern "C" int dalek_b200_edwards_msm_combine(dalek_b200_ctx *ctx, const uint64_t *windows, int ranks, size_t n_total,
-                                              uint8_t out_compressed[32], uint64_t out_limbs[20])
+extern "C" {
+
+int dalek_b200_edwards_msm_partial(dalek_b200_ctx *ctx, const uint8_t *scalars, const void *points, int point_fmt,
+                                   size_t n_local, size_t n_shard, uint64_t *out_windows)
 {
-    if (!ctx || !windows || ranks < 1 || ranks > 1024) return DALEK_E_INVALID_ARG;
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    int rc;
-    int c = msm_choose_window_bits(ctx, n_total);
-    int nwin = msm_window_count_for_bits(c);
-    size_t cnt = (size_t)ranks * nwin;
-    if ((rc = ws_reserve(ctx, ctx->misc1, cnt * 160))) return rc;
-    if ((rc = ws_reserve(ctx, ctx->misc0, cnt * sizeof(ge_p3_raw)))) return rc;
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->misc1.p, windows, cnt * 160, cudaMemcpyHostToDevice, ctx->stream));
-    k_limbs_to_windows<<<(unsigned)((cnt + 63) / 64), 64, 0, ctx->stream>>>((const uint64_t *)ctx->misc1.p, (int)cnt, (ge_p3_raw *)ctx->misc0.p);
-    ctx->launches++;
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
-    return finish_msm(ctx, (const ge_p3_raw *)ctx->misc0.p, ranks, n_total, out_compressed, out_limbs, nullptr);
+    return partial_common(ctx, scalars, points, false, point_fmt, n_local, n_shard, out_windows);
 }
+
+int dalek_b200_edwards_msm_partial_dev(dalek_b200_ctx *ctx, const void *d_scalars, const void *d_points, int point_fmt,
+                                       size_t n_local, size_t n_shard, uint64_t *out_windows)
+{
+    return partial_common(ctx, d_scalars, d_points, true, point_fmt, n_local, n_shard, out_windows);
+}
+
+int dalek_b200_edwards_msm_partial_async(dalek_b200_ctx *ctx, const uint8_t *scalars, const void *points, int point_fmt,
+                                         size_t n_local, size_t n_shard, void *d_out_record)
+{
+    return partial_async_common(ctx, scalars, points, false, point_fmt, n_local, n_shard, d_out_record);
+}
+
+int dalek_b200_edwards_msm_partial_dev_async(dalek_b200_ctx *ctx, const void *d_scalars, const void *d_points, int point_fmt,
+                                             size_t n_local, size_t n_shard, void *d_out_record)
+{
+    return partial_async_common(ctx, d_scalars, d_points, true, point_fmt, n_local, n_shard, d_out_record);
+}
+
+int dalek_b200_edwards_msm_combine(dalek_b200_ctx *ctx, const uint64_t *windows, int ranks, size_t n_shard,
+                                   uint8_t out_compressed[32], uint64_t out_limbs[20])
+{
+    if (!ctx) return DALEK_E_INVALID_ARG;
+    const size_t rec = (size_t)msm_window_count_for_bits(msm_choose_window_bits(ctx, n_shard)) * 160;   // no status words
+    return combine_common(ctx, windows, false, rec, ranks, n_shard, out_compressed, out_limbs);
+}
+
+int dalek_b200_edwards_msm_combine_dev(dalek_b200_ctx *ctx, const void *d_records, int ranks, size_t n_shard,
+                                       uint8_t out_compressed[32], uint64_t out_limbs[20])
+{
+    if (!ctx) return DALEK_E_INVALID_ARG;
+    return combine_common(ctx, d_records, true, dalek_b200_msm_partial_bytes(ctx, n_shard), ranks, n_shard, out_compressed, out_limbs);
+}
+
+}  // extern "C"

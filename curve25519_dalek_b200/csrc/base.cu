@@ -162,6 +162,7 @@ int ed25519_b200_sign_batch_flat(dalek_b200_ctx *ctx, const uint8_t *seeds, cons
     cudaStream_t st = ctx->stream;
     if ((rc = base_table_ensure(ctx))) return rc;
     if (!n) return 0;
+    for (size_t i = 0; i < n; i++) if (msg_offsets[i] > msg_offsets[i + 1]) return DALEK_E_INVALID_ARG;   // offsets must not decrease
     size_t mbytes = (size_t)msg_offsets[n];
     if ((rc = ws_reserve(ctx, ctx->scalars, n * 32))) return rc;
     if ((rc = ws_reserve(ctx, ctx->misc1, mbytes + 16))) return rc;

@@ -2,8 +2,8 @@
 //
 //   k_hram        one thread per signature: SHA-512(R || A || M) (batch.rs:179-191), h_i = hash mod l
 //                 (batch.rs:213-216), canonical-s check (batch.rs:208-211, signature.rs:89-94)
-//   k_transcript  one thread per chunk of `verify_chunk` signatures: the Merlin transcript of
-//                 batch.rs:168-205 and the 16-byte z_i draws of batch.rs:219-222
+//   k_transcript  the Merlin transcript of batch.rs:168-205 and the 16-byte z_i draws of batch.rs:219-222: ONE transcript
+//                 over the whole batch (the reference's, default) or -- opt-in `verify_chunk` -- one thread per chunk
 //   k_coeffs      one thread per signature: z_i*s_i and z_i*h_i mod l (batch.rs:225-233)
 //   k_sum_*       B_coefficient = sum z_i s_i, negated (batch.rs:225-230, :241)
 //   k_prep_*      R_i / A_i decompression (batch.rs:235-236, verifying.rs:167-175) into Niels form
@@ -280,7 +280,10 @@ k_key_accumulate(const uint32_t *__restrict__ zh, const uint32_t *__restrict__ r
     for (int k = 0; k < 8; k++) atomicAdd(a + k, (unsigned long long)zh[8 * i + k]);
 }
 
-// carry the eight counters of a key into one integer (< 2^287) and reduce it mod l
+// carry the eight counters of a key into one integer S = sum of its c_i = (z_i h_i mod l)  (< 2^287) and reduce it
+// modulo 8 l, the exponent of the WHOLE curve group: the reference adds [c_i] A for every signature (batch.rs:240-244),
+// and sum [c_i] A = [S] A = [S mod 8l] A also when A carries a small-order component, which a reduction mod l would
+// not preserve (l = 5 mod 8).  S mod 8l = 8 ((S >> 3) mod l) + (S & 7) < 2^256.
 __global__ void k_key_finalize(const unsigned long long *__restrict__ acc, size_t nkeys, uint32_t *__restrict__ out)
 {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -297,8 +300,15 @@ __global__ void k_key_finalize(const unsigned long long *__restrict__ acc, size_
     x[8] = (uint32_t)carry; x[9] = (uint32_t)(carry >> 32);
 #pragma unroll
     for (int k = 10; k < 16; k++) x[k] = 0;
+    const uint32_t low3 = x[0] & 7u;
+#pragma unroll
+    for (int k = 0; k < 15; k++) x[k] = (x[k] >> 3) | (x[k + 1] << 29);
+    x[15] >>= 3;
     uint32_t r[8];
-    sc_reduce512(r, x);
+    sc_reduce512(r, x);                                     // < l < 2^253
+#pragma unroll
+    for (int k = 7; k > 0; k--) r[k] = (r[k] << 3) | (r[k - 1] >> 29);
+    r[0] = (r[0] << 3) | low3;
 #pragma unroll
     for (int k = 0; k < 8; k++) out[8 * j + k] = r[k];
 }
@@ -368,17 +378,22 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
 {
     cudaStream_t st = (piece & 1) ? ctx->stream3 : ctx->stream, st2 = ctx->stream2;
     const size_t cnt = i1 - i0;
+    // verify_chunk = 0 (default): ONE transcript over the whole batch, the reference's (batch.rs:168-222); it needs every
+    // hram first, so it runs in verify_whole_transcript after the last piece.  > 0: one transcript per chunk (opt-in).
     const uint32_t chunk = (uint32_t)ctx->opt_verify_chunk;
     if (ready) { CUDA_TRY(ctx, cudaStreamWaitEvent(st, ready, 0)); CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ready, 0)); }
     if (cnt) {
         // the hashing -> transcript chain has little parallelism in its second stage: enqueue it first
         k_hram<<<cdiv(cnt, 128), 128, 0, st>>>(d_msgs, d_offs + i0, d_sigs + 16 * i0, d_keys + 8 * i0, cnt, b.hrams + 16 * i0,
                                                b.hs + 8 * i0, b.flags, b.bad_s + i0);
-        size_t nchunks = (cnt + chunk - 1) / chunk;
+        ctx->launches++;
         trace_mark(ctx, "hram done (hash stream)", st);
-        k_transcript<<<cdiv(nchunks, 64), 64, 0, st>>>(b.hrams + 16 * i0, d_sigs + 16 * i0, cnt, chunk, b.zs + 4 * i0);
-        ctx->launches += 2;
-        trace_mark(ctx, "transcript done (hash stream)", st);
+        if (chunk) {
+            size_t nchunks = (cnt + chunk - 1) / chunk;
+            k_transcript<<<cdiv(nchunks, 64), 64, 0, st>>>(b.hrams + 16 * i0, d_sigs + 16 * i0, cnt, chunk, b.zs + 4 * i0);
+            ctx->launches++;
+            trace_mark(ctx, "transcript done (hash stream)", st);
+        }
     }
     ge_niels_packed *points_A = b.points + 1;
     if (ctx->opt_decompress_f64)
@@ -400,7 +415,7 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
         else k_prep_A<0><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, nullptr, nullptr, nullptr, i0, cnt, points_A, b.flags, b.bad_key);
         ctx->launches++;
     }
-    if (cnt) {
+    if (cnt && chunk) {
         // with key merging z_i h_i replaces h_i in place and is summed per key in verify_tail
         uint32_t *out_zh = ctx->opt_dedupe_keys ? b.hs + 8 * i0 : b.scalars + 8 * (1 + i0);
         k_coeffs<<<cdiv(cnt, 128), 128, 0, st>>>(b.zs + 4 * i0, d_sigs + 16 * i0, b.hs + 8 * i0, cnt, b.scalars + 8 * (1 + n + i0),
@@ -409,6 +424,24 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
         trace_mark(ctx, "coeffs done (hash stream)", st);
     }
     trace_mark(ctx, "keys done (decompress stream)", st2);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+// verify_chunk = 0: the reference's single transcript over all n signatures (batch.rs:168-222) -- a strictly
+// sequential sponge (1.73 Keccak permutations per signature), one thread -- then the coefficients.  Runs on the main
+// stream after the hashing of every piece.
+static int verify_whole_transcript(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint32_t *d_sigs, size_t n)
+{
+    if (ctx->opt_verify_chunk || !n) return 0;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join2, ctx->stream3));           // odd pieces hash on stream3
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join2, 0));
+    k_transcript<<<1, 64, 0, st>>>(b.hrams, d_sigs, n, (uint32_t)std::min<size_t>(n, 0xffffffffu), b.zs);
+    trace_mark(ctx, "whole-batch transcript done (hash stream)", st);
+    uint32_t *out_zh = ctx->opt_dedupe_keys ? b.hs : b.scalars + 8;
+    k_coeffs<<<cdiv(n, 128), 128, 0, st>>>(b.zs, d_sigs, b.hs, n, b.scalars + 8 * (1 + n), out_zh, b.zsprod);
+    ctx->launches += 2;
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
@@ -561,6 +594,7 @@ static int verify_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t
     CUDA_TRY(ctx, cudaMemsetAsync(b.flags, 0, 64, ctx->stream));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     if ((rc = verify_front(ctx, b, d_msgs, d_offs, d_sigs, d_keys, n, 0, n, ctx->ev_fork))) return rc;
+    if ((rc = verify_whole_transcript(ctx, b, d_sigs, n))) return rc;
     return batch ? verify_batches_tail(ctx, b, n, 1, batch, verdicts) : verify_tail(ctx, b, n, 1);
 }
 
@@ -621,6 +655,7 @@ static int verify_host(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint
     int rc;
     size_t mbytes = n ? (size_t)msg_offsets[n] : 0;
     if (n && msg_offsets[0] != 0) return DALEK_E_INVALID_ARG;
+    for (size_t i = 0; i < n; i++) if (msg_offsets[i] > msg_offsets[i + 1]) return DALEK_E_INVALID_ARG;   // a negative length would read outside the staging buffer
     if ((rc = ws_reserve(ctx, ctx->misc1, mbytes + 16))) return rc;
     if ((rc = ws_reserve(ctx, ctx->msg_offs, (n + 1) * 8))) return rc;
     if ((rc = ws_reserve(ctx, ctx->points_in, std::max<size_t>(1, n) * 96))) return rc;   // sigs + keys
@@ -634,7 +669,7 @@ static int verify_host(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint
     CUDA_TRY(ctx, cudaStreamWaitEvent(sc, ctx->ev_fork, 0));
     // stream the batch in up to 8 pieces (boundaries on verify_chunk multiples): the copy of piece k+1
     // overlaps hashing / decompression of piece k
-    const size_t vc = (size_t)ctx->opt_verify_chunk;
+    const size_t vc = (size_t)std::max<long>(1, ctx->opt_verify_chunk);
     int K = n >= (1u << 18) ? (int)std::min<long>(8, std::max<long>(1, ctx->opt_verify_pieces)) : 1;
     size_t prev = 0;
     for (int k = 0; k < K; k++) {
@@ -651,6 +686,7 @@ static int verify_host(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_grp[k], sc));
         if ((rc = verify_front(ctx, b, d_msgs, d_offs, (const uint32_t *)d_sigs, (const uint32_t *)d_keys, n, i0, i1, ctx->ev_grp[k], k))) return rc;
     }
+    if ((rc = verify_whole_transcript(ctx, b, (const uint32_t *)d_sigs, n))) return rc;
     return batch ? verify_batches_tail(ctx, b, n, K, batch, verdicts) : verify_tail(ctx, b, n, K);
 }
 

@@ -30,7 +30,7 @@ struct dalek_b200_ctx {
     uint64_t launches = 0;
     // options
     long opt_window_bits = 0;
-    long opt_verify_chunk = 64;
+    long opt_verify_chunk = 0;     // 0: the reference's single transcript over the whole batch; k > 0: opt-in, one transcript per k signatures
     long opt_host_chunks = 4;   // host-buffer MSM calls stream the pairs in this many chunks (copy/compute overlap)
     long opt_trace = 0;            // 1: print a per-stage device timeline of verify_batch calls to stderr (diagnostics)
     long opt_precomp_tables = 0;   // 1: precomputations of >= 4096 points also keep 2^(cw) P tables (one bucket window, no doublings)
@@ -43,6 +43,7 @@ struct dalek_b200_ctx {
     float last_kernel_ms = 0.f;
     float last_call_ms = 0.f;
     int last_kernel_launches = 0;
+    bool async_open = false;       // a ..._partial_async call is in flight: its device span ends in ..._combine_dev
     // device workspaces (grown on demand, reused across calls)
     DevBuf scalars, points_in, points, digits, counts, offsets, sorted, buckets, red_a, red_b, red_c,
         red_d, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums, msg_offs, sum_desc, sum_part, key_table, key_acc, task_order, sig_status, misc6;

@@ -33,6 +33,7 @@
 #include "engine.h"
 #include "ge64.cuh"
 #include "warp4.cuh"
+#include "warp4_f64.cuh"
 
 // ------------------------------------------------------------------------------------------
 static inline unsigned cdiv(size_t a, unsigned b) { return (unsigned)((a + b - 1) / b); }
@@ -507,6 +508,54 @@ k_heavy_fixup(const uint32_t *__restrict__ heavy, const uint32_t *__restrict__ n
     }
 }
 
+// r = p + q for two extended points on the FP64 field: q -> projective Niels on the fly (edwards.rs:528-535), 9M
+__device__ __forceinline__ void ge64_add_p3(ge64_p3 &r, const ge64_p3 &p, const ge64_p3 &q, const fe64 &d2)
+{
+    ge64_pniels pn;
+    fe64_add(pn.YpX, q.Y, q.X);                            // 2
+    fe64_sub(pn.YmX, q.Y, q.X);                            // 2
+    pn.Z = q.Z;
+    fe64_mul(pn.T2d, q.T, d2);
+    ge64_padd(r, p, pn, 0u);
+}
+__device__ __forceinline__ void load_p3_f64(ge64_p3 &o, const ge_p3_raw *src)
+{
+    ge_p3 q; load_p3(q, src);
+    fe64_from_fe_limbs(o.X, q.X); fe64_from_fe_limbs(o.Y, q.Y); fe64_from_fe_limbs(o.Z, q.Z); fe64_from_fe_limbs(o.T, q.T);
+}
+
+// Level 1 of the bucket reduction (see k_chunk_reduce below) with ONE THREAD per chunk of m buckets on the
+// FP64-pipe field: 2^(c-1) W / m chunks (32768 for 2^20 pairs) are enough threads for the throughput field, and
+// a thread's 2(m-1) additions need no shuffles.  S_q = sum_r B_{qm+r},  W_q = sum_r (r+1) B_{qm+r}.
+__global__ void __launch_bounds__(64)
+k_chunk_reduce_f64(const ge_p3_raw *__restrict__ S_in, uint32_t n_in, uint32_t m, uint32_t n_out, uint32_t nwin,
+                   ge_p3_raw *__restrict__ S_out, ge_p3_raw *__restrict__ W_out)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_out * nwin) return;
+    const uint32_t w = t / n_out, q = t % n_out;
+    const ge_p3_raw *S = S_in + (size_t)w * n_in + (size_t)q * m;
+    fe64 d2; { fe k; fe_const_2d(k); fe64_from_fe_limbs(d2, k); }
+    ge64_p3 run, acc, x;
+    load_p3_f64(run, S + (m - 1));
+    acc = run;
+#pragma unroll 1
+    for (uint32_t r = m - 1; r-- > 0;) {
+        load_p3_f64(x, S + r);
+        ge64_add_p3(run, run, x, d2);
+        ge64_add_p3(acc, acc, run, d2);
+    }
+    ge_p3 o; ge_p3_raw raw;
+    ge64_to_p3(o, run); ge_p3_store_raw(raw, o);
+    uint4 *d = reinterpret_cast<uint4 *>(S_out + t);
+#pragma unroll
+    for (int k = 0; k < 10; k++) d[k] = make_uint4(raw.w[4 * k], raw.w[4 * k + 1], raw.w[4 * k + 2], raw.w[4 * k + 3]);
+    ge64_to_p3(o, acc); ge_p3_store_raw(raw, o);
+    d = reinterpret_cast<uint4 *>(W_out + t);
+#pragma unroll
+    for (int k = 0; k < 10; k++) d[k] = make_uint4(raw.w[4 * k], raw.w[4 * k + 1], raw.w[4 * k + 2], raw.w[4 * k + 3]);
+}
+
 // Bucket reduction  sum_b (b+1) B_b  per window (pippenger.rs:146-151), in log depth:
 //   level 1   chunks of m buckets: S_q = sum_r B_{qm+r},  W_q = sum_r (r+1) B_{qm+r}   (running sums)
 //   level l   chunks of m items of S^{l-1}: S^l_q, W^l_q = sum_r r S^{l-1}_{qm+r}      (0-based weights)
@@ -604,20 +653,25 @@ k_finish_windows(const ge_p3_raw *__restrict__ S_top, const ge_p3_raw *__restric
 }
 
 // Final Horner over windows (pippenger.rs:159): total = total * 2^c + window, ~250 sequential
-// doublings on one 4-lane group, then encode.
+// doublings on one 4-lane group over the FP64 field (warp4_f64.cuh), then encode.
 __global__ void __launch_bounds__(32)
 k_combine(const ge_p3_raw *__restrict__ windows, int ranks, int nwin, int c, MsmResult *__restrict__ res)
 {
     const uint32_t role = threadIdx.x & 3;
-    w4_point tot, x;
-    w4_identity(tot);
+    fe64 d2; { fe k; fe_const_2d(k); fe64_from_fe_limbs(d2, k); }
+    w4f_point tot, x;
+    w4f_identity(tot);
+#pragma unroll 1
     for (int w = nwin - 1; w >= 0; w--) {
-        if (w != nwin - 1)
-            for (int k = 0; k < c; k++) w4_dbl(tot, role, k == c - 1);
-        for (int r = 0; r < ranks; r++) { w4_load(x, windows + (size_t)r * nwin + w); w4_add(tot, x, role); }
+        if (w != nwin - 1) {
+#pragma unroll 1
+            for (int k = 0; k < c; k++) w4f_dbl(tot, role, k == c - 1);
+        }
+#pragma unroll 1
+        for (int r = 0; r < ranks; r++) { w4f_load(x, windows + (size_t)r * nwin + w); w4f_add(tot, x, d2, role); }
     }
     if (threadIdx.x != 0) return;
-    ge_p3 total; total.X = tot.X; total.Y = tot.Y; total.Z = tot.Z; total.T = tot.T;
+    ge_p3 total; w4f_to_p3(total, tot);
     uint32_t s[8];
     ge_compress(s, total);
 #pragma unroll
@@ -754,7 +808,10 @@ int msm_reduce_finish(dalek_b200_ctx *ctx, int c, ge_p3_raw *d_windows, MsmResul
     for (int l = 0; l < li.nlevels; l++) {
         uint32_t m = lvl_m[l], n_out = lvl_nout[l];
         ge_p3_raw *S_out = pool + pos, *W_out = pool + pos + (size_t)n_out * nwin;
-        k_chunk_reduce<<<cdiv((size_t)n_out * nwin * 4, 128), 128, 0, st>>>(S_in, n_in, m, l == 0 ? 1u : 0u, n_out, nwin, S_out, W_out);
+        if (l == 0 && ctx->opt_field_f64 && n_in % m == 0)
+            k_chunk_reduce_f64<<<cdiv((size_t)n_out * nwin, 64), 64, 0, st>>>(S_in, n_in, m, n_out, nwin, S_out, W_out);
+        else
+            k_chunk_reduce<<<cdiv((size_t)n_out * nwin * 4, 128), 128, 0, st>>>(S_in, n_in, m, l == 0 ? 1u : 0u, n_out, nwin, S_out, W_out);
         ctx->launches++;
         w_arrays.push_back({pos + (size_t)n_out * nwin, n_out});
         S_in = S_out; n_in = n_out; pos += 2 * (size_t)n_out * nwin;

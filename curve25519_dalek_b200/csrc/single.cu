@@ -178,6 +178,7 @@ int ed25519_b200_verify_each_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat,
 {
     if (!ctx || (n && (!msg_offsets || !sigs || !pubkeys || !results))) return DALEK_E_INVALID_ARG;
     if (n && msg_offsets[0] != 0) return DALEK_E_INVALID_ARG;
+    for (size_t i = 0; i < n; i++) if (msg_offsets[i] > msg_offsets[i + 1]) return DALEK_E_INVALID_ARG;   // offsets must not decrease
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CallTimer timer(ctx);
     int rc;

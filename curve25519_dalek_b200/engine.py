@@ -42,6 +42,13 @@ def load_library():
     lib.dalek_b200_edwards_msm_partial.argtypes = [vp, vp, vp, C.c_int, sz, sz, vp]
     lib.dalek_b200_edwards_msm_partial_dev.argtypes = [vp, vp, vp, C.c_int, sz, sz, vp]
     lib.dalek_b200_edwards_msm_combine.argtypes = [vp, vp, C.c_int, sz, vp, vp]
+    lib.dalek_b200_edwards_msm_combine_dev.argtypes = [vp, vp, C.c_int, sz, vp, vp]
+    lib.dalek_b200_edwards_msm_partial_async.argtypes = [vp, vp, vp, C.c_int, sz, sz, vp]
+    lib.dalek_b200_edwards_msm_partial_dev_async.argtypes = [vp, vp, vp, C.c_int, sz, sz, vp]
+    lib.dalek_b200_msm_partial_bytes.argtypes = [vp, sz]
+    lib.dalek_b200_msm_partial_bytes.restype = sz
+    lib.dalek_b200_stream.argtypes = [vp]
+    lib.dalek_b200_stream.restype = vp
     lib.dalek_b200_ristretto_double_base_batch.argtypes = [vp, vp, vp, vp, vp, sz, vp]
     lib.dalek_b200_ristretto_vartime_msm.argtypes = [vp, vp, vp, sz, vp]
     lib.ed25519_b200_verify_batch.argtypes = [vp, vp, vp, vp, vp, sz]
@@ -169,23 +176,46 @@ class Engine:
                                                             C.addressof(out), C.addressof(limbs) if want_limbs else None))
         return rc, bytes(out), (list(limbs) if want_limbs else None)
 
-    def msm_window_count(self, n_total):
-        return self._check(self.lib.dalek_b200_msm_window_count(self.h, n_total))
+    # ---- sharded MSM: n_shard = size of the largest shard, the same on every rank (it selects the window width) ----
+    def msm_window_count(self, n_shard):
+        return self._check(self.lib.dalek_b200_msm_window_count(self.h, n_shard))
 
-    def edwards_msm_partial(self, scalars, points, n_local, n_total, point_fmt=POINTS_COMPRESSED, device_ptrs=False):
-        nwin = self.msm_window_count(n_total)
+    def msm_partial_bytes(self, n_shard):
+        """Bytes of a shard's device record (window accumulators + status word)."""
+        return int(self.lib.dalek_b200_msm_partial_bytes(self.h, n_shard))
+
+    def stream_ptr(self):
+        """The context's main cudaStream_t as an integer (torch.cuda.ExternalStream(ptr))."""
+        return int(self.lib.dalek_b200_stream(self.h) or 0)
+
+    def edwards_msm_partial(self, scalars, points, n_local, n_shard, point_fmt=POINTS_COMPRESSED, device_ptrs=False):
+        nwin = self.msm_window_count(n_shard)
         out = (C.c_uint64 * (20 * nwin))()
         fn = self.lib.dalek_b200_edwards_msm_partial_dev if device_ptrs else self.lib.dalek_b200_edwards_msm_partial
-        rc = self._check(fn(self.h, _ptr(scalars), _ptr(points), point_fmt, n_local, n_total, C.addressof(out)))
+        rc = self._check(fn(self.h, _ptr(scalars), _ptr(points), point_fmt, n_local, n_shard, C.addressof(out)))
         return rc, out
 
-    def edwards_msm_combine(self, windows, ranks, n_total, want_limbs=False):
+    def edwards_msm_combine(self, windows, ranks, n_shard, want_limbs=False):
         out = (C.c_uint8 * 32)()
         limbs = (C.c_uint64 * 20)() if want_limbs else None
         self._check(self.lib.dalek_b200_edwards_msm_combine(self.h, _ptr(windows) if not isinstance(windows, C.Array) else C.addressof(windows),
-                                                            ranks, n_total, C.addressof(out),
+                                                            ranks, n_shard, C.addressof(out),
                                                             C.addressof(limbs) if want_limbs else None))
         return bytes(out), (list(limbs) if want_limbs else None)
+
+    def edwards_msm_partial_async(self, scalars, points, n_local, n_shard, d_out_record, point_fmt=POINTS_COMPRESSED,
+                                  device_ptrs=False):
+        """Enqueue the shard's MSM on the context's stream; its record lands in the device buffer d_out_record."""
+        fn = self.lib.dalek_b200_edwards_msm_partial_dev_async if device_ptrs else self.lib.dalek_b200_edwards_msm_partial_async
+        return self._check(fn(self.h, _ptr(scalars), _ptr(points), point_fmt, n_local, n_shard, _ptr(d_out_record)))
+
+    def edwards_msm_combine_dev(self, d_records, ranks, n_shard, want_limbs=False):
+        """(rc, compressed, limbs) from `ranks` gathered device records; rc 1 == None."""
+        out = (C.c_uint8 * 32)()
+        limbs = (C.c_uint64 * 20)() if want_limbs else None
+        rc = self._check(self.lib.dalek_b200_edwards_msm_combine_dev(self.h, _ptr(d_records), ranks, n_shard, C.addressof(out),
+                                                                     C.addressof(limbs) if want_limbs else None))
+        return rc, bytes(out), (list(limbs) if want_limbs else None)
 
     # ---- Ristretto ----
     def ristretto_double_base_batch(self, a, b, G, H, n, out=None):

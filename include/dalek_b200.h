@@ -108,23 +108,47 @@ int dalek_b200_edwards_vartime_msm_dev(dalek_b200_ctx *ctx, const void *d_scalar
                                        int point_fmt, size_t n, uint8_t out_compressed[32],
                                        uint64_t out_limbs[20]);
 
-/* -------- sharded MSM (one call per GPU / rank) -------------------------------- */
-/* Number of window accumulators a partial MSM over `n_total` pairs produces (all ranks must
- * pass the same n_total so that the window width agrees). */
-int dalek_b200_msm_window_count(dalek_b200_ctx *ctx, size_t n_total);
-/* Partial MSM over this rank's shard: writes `window_count` window accumulators
- * (each 20 x u64 extended limbs, window 0 = least significant) to out_windows (host). */
+/* -------- sharded MSM (one call per GPU / rank) --------------------------------
+ * MSM is linear: every rank reduces a contiguous shard of the pairs to one accumulator per bucket window
+ * (pippenger.rs:146-151 for its shard), the accumulators are exchanged once (all-gather: point addition is
+ * not an NCCL reduction operator), and every rank adds them per window and runs the Horner pass of
+ * pippenger.rs:159.  `n_shard` is the size of the LARGEST shard (ceil(n_total / ranks) for an even split)
+ * and must be the same on every rank: the window width is chosen from it, i.e. for the work one GPU does.
+ *
+ * Number of window accumulators of a partial MSM for that shard size. */
+int dalek_b200_msm_window_count(dalek_b200_ctx *ctx, size_t n_shard);
+/* Size in bytes of a shard's device RECORD: window_count x 20 u64 limbs, then one u64 status word
+ * (non-zero: a compressed point of the shard did not decode -> the combined result is None). */
+size_t dalek_b200_msm_partial_bytes(dalek_b200_ctx *ctx, size_t n_shard);
+/* Partial MSM over this rank's shard, blocking: writes `window_count` window accumulators
+ * (each 20 x u64 extended limbs, window 0 = least significant) to out_windows (host).
+ * DALEK_NONE if a compressed point did not decode. */
 int dalek_b200_edwards_msm_partial(dalek_b200_ctx *ctx, const uint8_t *scalars, const void *points,
-                                   int point_fmt, size_t n_local, size_t n_total,
+                                   int point_fmt, size_t n_local, size_t n_shard,
                                    uint64_t *out_windows);
 int dalek_b200_edwards_msm_partial_dev(dalek_b200_ctx *ctx, const void *d_scalars, const void *d_points,
-                                       int point_fmt, size_t n_local, size_t n_total,
+                                       int point_fmt, size_t n_local, size_t n_shard,
                                        uint64_t *out_windows);
-/* Combine the gathered accumulators of `ranks` shards (rank-major: ranks x window_count x 20 u64)
+/* Combine the gathered accumulators of `ranks` shards (host, rank-major: ranks x window_count x 20 u64)
  * into the final point: per-window sum over ranks, then total = total * 2^w + window
  * (pippenger.rs:159). */
 int dalek_b200_edwards_msm_combine(dalek_b200_ctx *ctx, const uint64_t *windows, int ranks,
-                                   size_t n_total, uint8_t out_compressed[32], uint64_t out_limbs[20]);
+                                   size_t n_shard, uint8_t out_compressed[32], uint64_t out_limbs[20]);
+/* The same exchange without leaving the device: ..._partial[_dev]_async ENQUEUES the shard's MSM on the
+ * context's stream and writes its record (dalek_b200_msm_partial_bytes) to the device buffer d_out_record;
+ * it returns without synchronising.  The caller enqueues the all-gather of the records behind it ON THAT
+ * STREAM (dalek_b200_stream: e.g. torch.cuda.ExternalStream + torch.distributed.all_gather_into_tensor, or
+ * ncclAllGather(..., stream)), then ..._combine_dev takes the gathered device buffer (ranks records,
+ * rank-major), runs the Horner pass and blocks only for the 192-byte result.  DALEK_NONE if any shard's
+ * status word is set.  dalek_b200_last_call_ms then spans partial + exchange + combine on the device. */
+int dalek_b200_edwards_msm_partial_async(dalek_b200_ctx *ctx, const uint8_t *scalars, const void *points,
+                                         int point_fmt, size_t n_local, size_t n_shard, void *d_out_record);
+int dalek_b200_edwards_msm_partial_dev_async(dalek_b200_ctx *ctx, const void *d_scalars, const void *d_points,
+                                             int point_fmt, size_t n_local, size_t n_shard, void *d_out_record);
+int dalek_b200_edwards_msm_combine_dev(dalek_b200_ctx *ctx, const void *d_records, int ranks, size_t n_shard,
+                                       uint8_t out_compressed[32], uint64_t out_limbs[20]);
+/* The context's main CUDA stream (a cudaStream_t) for callers that order their own work with the engine's. */
+void *dalek_b200_stream(dalek_b200_ctx *ctx);
 
 /* -------- VartimePrecomputedMultiscalarMul ---------------------------------
  * C/traits.rs:290-406; VartimeEdwardsPrecomputation C/edwards.rs:1038-1076, VartimeRistrettoPrecomputation

@@ -208,6 +208,20 @@ int ed25519_verify_strict(const uint8_t *msg, size_t len, const uint8_t sig[64],
 void ed25519_public_key(uint8_t pk[32], const uint8_t seed[32]);
 void ed25519_sign(uint8_t sig[64], const uint8_t *msg, size_t len, const uint8_t seed[32]);
 
+/* ---------------- parallel.c: persistent worker threads over independent slices (bench infrastructure) ---------- */
+typedef struct oracle_pool oracle_pool;
+oracle_pool *oracle_pool_create(int threads);
+void oracle_pool_destroy(oracle_pool *pool);
+int oracle_pool_threads(const oracle_pool *pool);
+/* each returns the wall time of the job in seconds */
+double oracle_pool_msm(oracle_pool *pool, uint8_t out[32], const uint8_t *scalars, const ge_p3 *points, size_t n, size_t slice);
+double oracle_pool_verify_batches(oracle_pool *pool, const uint8_t *msgs, size_t msg_len, const uint8_t *sigs,
+                                  const uint8_t *keys, size_t n, size_t batch, int *verdicts);
+double oracle_pool_verify_each(oracle_pool *pool, const uint8_t *msgs, size_t msg_len, const uint8_t *sigs,
+                               const uint8_t *keys, size_t n, int strict, uint8_t *results);
+double oracle_pool_double_base(oracle_pool *pool, uint8_t *out, const uint8_t *a, const uint8_t *b, const uint8_t G[32],
+                               const uint8_t H[32], size_t n, int *ok);
+
 #ifdef __cplusplus
 }
 #endif

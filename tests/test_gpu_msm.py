@@ -106,22 +106,57 @@ def test_msm_skewed_buckets(eng, oracle):
 
 
 def test_msm_sharded_partial_combine(eng, oracle):
-    """contiguous shards -> window accumulators -> combine == single MSM."""
-    n, ranks = 1200, 4
+    """contiguous shards -> window accumulators -> combine == single MSM.  The window width comes from
+    the SHARD size (the work one GPU does), identical on every rank."""
+    from curve25519_dalek_b200.sharding import shard_range, shard_size
+    n, ranks = 1203, 4
     scalars, points = gen_case(oracle, n)
     comp = [oracle.compress(p) for p in points]
     want = oracle.compress(oracle.msm("optional", scalars, points))
-    nwin = eng.msm_window_count(n)
+    n_shard = shard_size(n, ranks)
+    nwin = eng.msm_window_count(n_shard)
+    assert eng.msm_partial_bytes(n_shard) == nwin * 160 + 8
     allw = (C.c_uint64 * (20 * nwin * ranks))()
-    per = n // ranks
     for r in range(ranks):
-        lo, hi = r * per, (r + 1) * per if r < ranks - 1 else n
-        rc, w = eng.edwards_msm_partial(b"".join(scalars[lo:hi]), b"".join(comp[lo:hi]), hi - lo, n)
+        lo, hi = shard_range(n, r, ranks)
+        rc, w = eng.edwards_msm_partial(b"".join(scalars[lo:hi]), b"".join(comp[lo:hi]), hi - lo, n_shard)
         assert rc == 0
         for k in range(20 * nwin):
             allw[r * 20 * nwin + k] = w[k]
-    got, _ = eng.edwards_msm_combine(allw, ranks, n)
+    got, _ = eng.edwards_msm_combine(allw, ranks, n_shard)
     assert got == want
+
+
+def test_msm_sharded_device_resident(eng, oracle):
+    """The same exchange without leaving the device: partial_async records -> (gathered) device buffer -> combine_dev.
+    Several shards are run one after another on this one GPU into slices of the gathered buffer."""
+    import torch
+    from curve25519_dalek_b200.sharding import shard_range, shard_size, ShardedMsm
+    n, ranks = 2500, 3
+    scalars, points = gen_case(oracle, n)
+    comp = [oracle.compress(p) for p in points]
+    want = oracle.compress(oracle.msm("optional", scalars, points))
+    n_shard = shard_size(n, ranks)
+    rec = eng.msm_partial_bytes(n_shard)
+    dev = torch.device("cuda", 0)
+    gathered = torch.zeros(ranks * rec, dtype=torch.uint8, device=dev)
+    for r in range(ranks):
+        lo, hi = shard_range(n, r, ranks)
+        assert eng.edwards_msm_partial_async(b"".join(scalars[lo:hi]), b"".join(comp[lo:hi]), hi - lo, n_shard,
+                                             gathered.data_ptr() + r * rec) == 0
+    rc, got, _ = eng.edwards_msm_combine_dev(gathered.data_ptr(), ranks, n_shard)
+    assert rc == 0 and got == want
+    # an undecodable point in one shard marks its record: the combined result is None
+    bad = list(comp); bad[n - 2] = (2).to_bytes(32, "little")         # y = 2 is not on the curve
+    for r in range(ranks):
+        lo, hi = shard_range(n, r, ranks)
+        eng.edwards_msm_partial_async(b"".join(scalars[lo:hi]), b"".join(bad[lo:hi]), hi - lo, n_shard, gathered.data_ptr() + r * rec)
+    rc, _, _ = eng.edwards_msm_combine_dev(gathered.data_ptr(), ranks, n_shard)
+    assert rc == 1
+    # world = 1 through the helper bench.py uses (the engine's stream as a torch ExternalStream)
+    sm = ShardedMsm(eng, 1, n, dev)
+    rc, got = sm.run(b"".join(scalars), b"".join(comp), n, 0, False)
+    assert rc == 0 and got == want and eng.last_call_ms() > 0
 
 
 def test_msm_large_algebraic_identity(eng, oracle):

@@ -31,7 +31,7 @@ def make_batch(oracle, n, seed=0, msg_len=None):
     return msgs, sigs, pks
 
 
-CHUNK = 64          # the engine's default verify_chunk (signatures per Merlin transcript)
+CHUNK = 0           # the engine's default verify_chunk: 0 = the reference's single transcript over the whole batch
 
 
 def run(eng, msgs, sigs, pks):
@@ -45,10 +45,7 @@ def test_verify_batch_valid_and_zs(eng, oracle, n):
     rc_o, zs_o = oracle.verify_batch(msgs, sigs, pks, chunk=chunk, want_zs=True)
     assert rc_o == OK
     assert run(eng, msgs, sigs, pks) == OK
-    assert eng.last_zs(n) == zs_o            # transcript parity (per chunk)
-    if 0 < n <= chunk:                        # single chunk: exactly the reference's transcript
-        rc_o, zs_ref = oracle.verify_batch(msgs, sigs, pks, want_zs=True)
-        assert zs_ref == zs_o
+    assert eng.last_zs(n) == zs_o            # every z_i is the reference's (one transcript over the whole batch)
 
 
 def test_verify_batch_chunk_option(eng, oracle):
@@ -60,7 +57,7 @@ def test_verify_batch_chunk_option(eng, oracle):
             rc, zs = oracle.verify_batch(msgs, sigs, pks, chunk=chunk, want_zs=True)
             assert eng.last_zs(50) == zs
         finally:
-            eng.set_option("verify_chunk", CHUNK)
+            eng.set_option("verify_chunk", 0)
 
 
 def test_verify_batch_negative_controls(eng, oracle):
@@ -99,9 +96,15 @@ def test_verify_batch_reference_fixtures(eng, oracle):
     assert run(eng, msgs, sigs, pks) == OK
     with open(os.path.join(ROOT, "tests", "golden", "ed25519_validation.json")) as f:
         vv = json.load(f)["vectors"]
-    for v in vv[::7]:
+    assert len(vv) == 914
+    for v in vv:                                                     # all 914 cases, each as a batch of one
         m, s_, k = [v["msg"].encode()], [H(v["sig"])], [H(v["key"])]
         assert run(eng, m, s_, k) == oracle.verify_batch(m, s_, k), v["number"]
+    # ... and all of them in ONE call as 914 independent batches of one signature
+    msgs = [v["msg"].encode() for v in vv]
+    flat, offs = _flat(msgs)
+    rc, verdicts = eng.verify_batches_flat(flat, offs, b"".join(H(v["sig"]) for v in vv), b"".join(H(v["key"]) for v in vv), len(vv), 1)
+    assert verdicts == [oracle.verify_batch([m], [H(v["sig"])], [H(v["key"])]) for m, v in zip(msgs, vv)]
 
 
 def test_verify_batch_python_api(eng, oracle):
@@ -131,6 +134,8 @@ def test_verify_batch_flat_large(eng, oracle):
     sg = np.frombuffer(b"".join(sigs), dtype=np.uint8).copy()
     pk = np.frombuffer(b"".join(keys[i % nk] for i in range(n)), dtype=np.uint8).copy()
     assert eng.verify_batch_flat(flat, offs, sg, pk, n) == OK
+    rc_o, zs_o = oracle.verify_batch(msgs, sigs, [keys[i % nk] for i in range(n)], want_zs=True)
+    assert rc_o == OK and eng.last_zs(n) == zs_o             # 20000 coefficients of the reference's single transcript
     flat[59 * 12345 + 7] ^= 1
     assert eng.verify_batch_flat(flat, offs, sg, pk, n) == VERIFY
 
@@ -153,6 +158,7 @@ def test_verify_batch_host_streaming_pieces(eng, oracle):
     for i in (0, 1, 70000, n - 1):                          # oracle spot checks of the synthesised inputs
         m = flat[int(offs[i]):int(offs[i + 1])].tobytes()
         assert oracle.verify(m, sg[64 * i:64 * i + 64].tobytes(), pk[32 * i:32 * i + 32].tobytes()) == OK
+    eng.set_option("verify_chunk", 64)                      # opt-in chunked transcripts: the piece sweep runs 6 calls
     for pieces in (4, 1, 3):
         eng.set_option("verify_pieces", pieces)
         try:
@@ -168,11 +174,14 @@ def test_verify_batch_host_streaming_pieces(eng, oracle):
         else:
             assert zs == zs4                                # the coefficients do not depend on the piece count
     # z_i of the first transcript chunk agree with the oracle's
-    first = CHUNK
+    first = 64
     msgs = [flat[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(first)]
     rc, zo = oracle.verify_batch(msgs, [sg[64 * i:64 * i + 64].tobytes() for i in range(first)],
-                                 [pk[32 * i:32 * i + 32].tobytes() for i in range(first)], chunk=CHUNK, want_zs=True)
+                                 [pk[32 * i:32 * i + 32].tobytes() for i in range(first)], chunk=64, want_zs=True)
     assert rc == OK and zs4[:16 * first] == zo
+    eng.set_option("verify_chunk", 0)
+    # default mode (one transcript over all 2^18 + 77 signatures, streamed in 4 pieces): verdict only
+    assert eng.verify_batch_flat(flat, offs, sg, pk, n) == OK
 
 
 def test_verify_batch_key_dedupe(eng, oracle):
@@ -335,3 +344,30 @@ def test_verify_batches_all_distinct_keys_with_failure(eng, oracle):
             assert v == want
         finally:
             eng.set_option("dedupe_keys", 1)
+
+
+# ---- small-order components: the verdict of the un-cofactored batch equation depends on the z_i (batch.rs:240-250) ----
+@pytest.mark.parametrize("n", [5, 100, 300])
+def test_verify_batch_mixed_order_components_match_reference(eng, oracle, n):
+    """Signatures whose R, or whose public key A, carries a small-order component leave a pure torsion defect in the
+    batch equation; Ok or Verify then depends on the z_i modulo 8 (R) and on (z_i h_i mod l) modulo 8 (A), so only the
+    reference's own coefficients -- ONE transcript over the whole batch, also for n > 64 -- and exact per-key scalar
+    sums (modulo 8 l, not l) give the reference's verdict.  tests/test_oracle_ed25519.py shows on the CPU that both
+    verdicts occur over these seeds and that chunked transcripts would disagree."""
+    import torsion_cases
+    outcomes = set()
+    for trial in range(10):
+        msgs, sigs, pks = torsion_cases.make_batch(oracle, n, seed=1000 * n + trial)
+        want = oracle.verify_batch(msgs, sigs, pks)
+        for dedupe in (1, 0):
+            eng.set_option("dedupe_keys", dedupe)
+            try:
+                assert run(eng, msgs, sigs, pks) == want, (trial, dedupe)
+            finally:
+                eng.set_option("dedupe_keys", 1)
+        # the same signatures as independent batches of 16: each verdict is the reference's for that batch alone
+        flat, offs = _flat(msgs)
+        rc, v = eng.verify_batches_flat(flat, offs, b"".join(sigs), b"".join(pks), n, 16)
+        assert v == [oracle.verify_batch(msgs[k:k + 16], sigs[k:k + 16], pks[k:k + 16]) for k in range(0, n, 16)], trial
+        outcomes.add(want)
+    assert outcomes <= {OK, VERIFY}

@@ -159,3 +159,19 @@ def test_verify_batch_zs_depend_on_inputs_and_chunking(oracle):
     rc, za = oracle.verify_batch(msgs[:4], sigs[:4], pks[:4], want_zs=True)
     rc, zb = oracle.verify_batch(msgs[4:], sigs[4:], pks[4:], want_zs=True)
     assert zc == za + zb and zc != z1
+
+
+def test_mixed_order_batches_have_z_dependent_verdicts(oracle):
+    """tests/torsion_cases.py (inputs of the GPU parity test for small-order components): over its seeds the reference
+    algorithm returns both Ok and Verify, and cutting the transcript into 64-signature chunks changes some verdicts --
+    which is why the engine's default is the reference's single transcript."""
+    import torsion_cases
+    verdicts, disagreements = set(), 0
+    for trial in range(10):
+        msgs, sigs, pks = torsion_cases.make_batch(oracle, 100, seed=1000 * 100 + trial)
+        whole = oracle.verify_batch(msgs, sigs, pks)
+        verdicts.add(whole)
+        disagreements += whole != oracle.verify_batch(msgs, sigs, pks, chunk=64)
+        # every signature is individually INVALID under `verify` only when its own defect is non-zero: the clean ones pass
+        assert oracle.verify(msgs[1], sigs[1], pks[1]) in (0, 1)
+    assert verdicts == {0, 1} and disagreements > 0
