@@ -9,10 +9,10 @@ touches the CPU checker used by the tests.  Names follow the reference:
   VartimeEdwardsPrecomputation / VartimeRistrettoPrecomputation (traits.rs:290-406, edwards.rs:1038-1076)
   verify_batch (ed25519-dalek/src/batch.rs:146-251) and its SignatureError values.
 """
-from .engine import (Engine, EngineError, EdwardsPoint, RistrettoPoint, SignatureError, verify_batch, default_engine,
+from .engine import (Engine, MultiEngine, EngineError, EdwardsPoint, RistrettoPoint, SignatureError, verify_batch, default_engine,
                      library_path, load_library, POINTS_COMPRESSED, POINTS_EXTENDED, POINTS_RISTRETTO,
                      VartimeEdwardsPrecomputation, VartimeRistrettoPrecomputation)
 
-__all__ = ["Engine", "EngineError", "EdwardsPoint", "RistrettoPoint", "SignatureError", "verify_batch", "default_engine",
+__all__ = ["Engine", "MultiEngine", "EngineError", "EdwardsPoint", "RistrettoPoint", "SignatureError", "verify_batch", "default_engine",
            "library_path", "load_library", "POINTS_COMPRESSED", "POINTS_EXTENDED", "POINTS_RISTRETTO",
            "VartimeEdwardsPrecomputation", "VartimeRistrettoPrecomputation"]

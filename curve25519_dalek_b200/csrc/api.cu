@@ -76,6 +76,7 @@ int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value)
     if (!strcmp(name, "double_base_comb")) { ctx->opt_double_base_comb = value ? 1 : 0; return 0; }
     if (!strcmp(name, "dedupe_keys")) { ctx->opt_dedupe_keys = value ? 1 : 0; return 0; }
     if (!strcmp(name, "verify_pieces")) { if (value < 1 || value > 8) return DALEK_E_INVALID_ARG; ctx->opt_verify_pieces = value; return 0; }
+    if (!strcmp(name, "acc_tma")) { ctx->opt_acc_tma = value ? 1 : 0; return 0; }
     if (!strcmp(name, "field_f64")) { ctx->opt_field_f64 = value ? 1 : 0; return 0; }
     if (!strcmp(name, "verify_chunk")) { if (value < 0 || value > (1 << 20)) return DALEK_E_INVALID_ARG; ctx->opt_verify_chunk = value; return 0; }
     return DALEK_E_INVALID_ARG;
@@ -293,8 +294,9 @@ static int partial_common(dalek_b200_ctx *ctx, const void *scalars, const void *
     return status ? DALEK_NONE : DALEK_OK;
 }
 
-static int partial_async_common(dalek_b200_ctx *ctx, const void *scalars, const void *points, bool on_device, int point_fmt,
-                                size_t n_local, size_t n_shard, void *d_out_record)
+// dst_device >= 0: d_out_record lives on that (other) device -- the record crosses NVLink as a peer copy
+int msm_partial_enqueue_record(dalek_b200_ctx *ctx, const void *scalars, const void *points, bool on_device, int point_fmt,
+                               size_t n_local, size_t n_shard, void *d_out_record, int dst_device)
 {
     if (!ctx || !d_out_record) return DALEK_E_INVALID_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -302,13 +304,16 @@ static int partial_async_common(dalek_b200_ctx *ctx, const void *scalars, const 
     ctx->async_open = true;
     int rc, nwin = 0;
     if ((rc = partial_enqueue(ctx, scalars, points, on_device, point_fmt, n_local, n_shard, &nwin))) return rc;
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_out_record, ctx->misc1.p, (size_t)nwin * 160 + 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (dst_device >= 0 && dst_device != ctx->device)
+        CUDA_TRY(ctx, cudaMemcpyPeerAsync(d_out_record, dst_device, ctx->misc1.p, ctx->device, (size_t)nwin * 160 + 8, ctx->stream));
+    else
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_out_record, ctx->misc1.p, (size_t)nwin * 160 + 8, cudaMemcpyDeviceToDevice, ctx->stream));
     return DALEK_OK;
 }
 
 // records (host or device) -> Horner over windows -> result read-back
-static int combine_common(dalek_b200_ctx *ctx, const void *records, bool on_device, size_t rec_bytes, int ranks, size_t n_shard,
-                          uint8_t out_compressed[32], uint64_t out_limbs[20])
+int msm_combine_records(dalek_b200_ctx *ctx, const void *records, bool on_device, size_t rec_bytes, int ranks, size_t n_shard,
+                        uint8_t out_compressed[32], uint64_t out_limbs[20])
 {
     if (!ctx || !records || ranks < 1 || ranks > 1024) return DALEK_E_INVALID_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -367,13 +372,13 @@ int dalek_b200_edwards_msm_partial_dev(dalek_b200_ctx *ctx, const void *d_scalar
 int dalek_b200_edwards_msm_partial_async(dalek_b200_ctx *ctx, const uint8_t *scalars, const void *points, int point_fmt,
                                          size_t n_local, size_t n_shard, void *d_out_record)
 {
-    return partial_async_common(ctx, scalars, points, false, point_fmt, n_local, n_shard, d_out_record);
+    return msm_partial_enqueue_record(ctx, scalars, points, false, point_fmt, n_local, n_shard, d_out_record, -1);
 }
 
 int dalek_b200_edwards_msm_partial_dev_async(dalek_b200_ctx *ctx, const void *d_scalars, const void *d_points, int point_fmt,
                                              size_t n_local, size_t n_shard, void *d_out_record)
 {
-    return partial_async_common(ctx, d_scalars, d_points, true, point_fmt, n_local, n_shard, d_out_record);
+    return msm_partial_enqueue_record(ctx, d_scalars, d_points, true, point_fmt, n_local, n_shard, d_out_record, -1);
 }
 
 int dalek_b200_edwards_msm_combine(dalek_b200_ctx *ctx, const uint64_t *windows, int ranks, size_t n_shard,
@@ -381,14 +386,14 @@ int dalek_b200_edwards_msm_combine(dalek_b200_ctx *ctx, const uint64_t *windows,
 {
     if (!ctx) return DALEK_E_INVALID_ARG;
     const size_t rec = (size_t)msm_window_count_for_bits(msm_choose_window_bits(ctx, n_shard)) * 160;   // no status words
-    return combine_common(ctx, windows, false, rec, ranks, n_shard, out_compressed, out_limbs);
+    return msm_combine_records(ctx, windows, false, rec, ranks, n_shard, out_compressed, out_limbs);
 }
 
 int dalek_b200_edwards_msm_combine_dev(dalek_b200_ctx *ctx, const void *d_records, int ranks, size_t n_shard,
                                        uint8_t out_compressed[32], uint64_t out_limbs[20])
 {
     if (!ctx) return DALEK_E_INVALID_ARG;
-    return combine_common(ctx, d_records, true, dalek_b200_msm_partial_bytes(ctx, n_shard), ranks, n_shard, out_compressed, out_limbs);
+    return msm_combine_records(ctx, d_records, true, dalek_b200_msm_partial_bytes(ctx, n_shard), ranks, n_shard, out_compressed, out_limbs);
 }
 
 }  // extern "C"

@@ -38,6 +38,7 @@ struct dalek_b200_ctx {
     long opt_dedupe_keys = 1;   // verify_batch decompresses every distinct public key once
     long opt_verify_pieces = 4; // host-buffer verify_batch calls stream the signatures in this many pieces
     long opt_decompress_f64 = 1; // square-root exponentiation of point decompression on the FP64-pipe field
+    long opt_acc_tma = 0;       // bucket kernel gathers points with TMA bulk copies + mbarriers instead of cp.async (A/B option)
     long opt_field_f64 = 1;     // bucket kernel on the FP64 pipe (fe64.cuh) instead of IMAD.WIDE (fe.cuh)
     // timing of the dominant kernel in the last call
     float last_kernel_ms = 0.f;
@@ -138,6 +139,15 @@ int msm_full(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_point
              ge_p3_raw *d_windows, MsmResult *d_result);
 int msm_combine_windows(dalek_b200_ctx *ctx, const ge_p3_raw *d_windows, int ranks, int nwin, int c,
                         MsmResult *d_result);
+
+// ---- sharded MSM building blocks (api.cu), shared with the single-process multi-GPU entry points (multi.cu) ----
+// Enqueue the MSM of one shard on ctx's stream; its record (window accumulators + status word) is copied to
+// d_out_record (on device dst_device if >= 0 and different from ctx's: a peer copy).  Nothing is synchronised.
+int msm_partial_enqueue_record(dalek_b200_ctx *ctx, const void *scalars, const void *points, bool on_device, int point_fmt,
+                               size_t n_local, size_t n_shard, void *d_out_record, int dst_device);
+// `ranks` records (host or device, rec_bytes apart) -> per-window sums, Horner, encode; blocks for the result.
+int msm_combine_records(dalek_b200_ctx *ctx, const void *records, bool on_device, size_t rec_bytes, int ranks, size_t n_shard,
+                        uint8_t out_compressed[32], uint64_t out_limbs[20]);
 
 // ---- constant-time Straus (straus.cu) ----
 int straus_ct_msm(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points_pniels, size_t n,

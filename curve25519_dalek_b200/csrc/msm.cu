@@ -379,7 +379,9 @@ __device__ __forceinline__ void load_p3(ge_p3 &p, const ge_p3_raw *src)
     ge_p3_load_raw(p, r);
 }
 
-template <int KIND, int F64>
+// TMA = 1: the gather of the next point is ONE bulk copy of the TMA unit (cp.async.bulk.shared.global, completion
+// on a per-thread mbarrier) instead of 6-8 16-byte cp.async (LDGSTS); see profiles/ for the A/B measurement.
+template <int KIND, int F64, int TMA>
 __global__ void __launch_bounds__(128, ACC_MIN_BLOCKS)
 k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict__ sorted,
                     const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets,
@@ -387,7 +389,12 @@ k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict_
                     const uint32_t *__restrict__ win_base, int w0, int w1, size_t n, uint32_t nbuckets, uint32_t task_len,
                     ge_p3_raw *__restrict__ buckets, ge_p3_raw *__restrict__ task_sums, int first)
 {
-    __shared__ uint4 s_pts[F64 ? 2 : 1][F64 ? 8 : 1][F64 ? 128 : 1];   // prefetch slots, [buffer][piece][thread]: conflict-free
+    constexpr int NQ = KIND == PK_NIELS ? 6 : 8;              // 16-byte pieces per point
+    constexpr int TSTRIDE = NQ * 16 + 16;                     // bulk copies land contiguously: pad the per-thread slot so
+                                                              // that the 16-byte reads of 8 consecutive threads hit 8 different bank groups
+    __shared__ uint4 s_pts[(F64 && !TMA) ? 2 : 1][(F64 && !TMA) ? 8 : 1][(F64 && !TMA) ? 128 : 1];   // cp.async slots, [buffer][piece][thread]: conflict-free
+    __shared__ __align__(16) unsigned char s_bulk[(F64 && TMA) ? 2 : 1][(F64 && TMA) ? 128 : 1][(F64 && TMA) ? TSTRIDE : 16];
+    __shared__ __align__(8) unsigned long long s_bar[(F64 && TMA) ? 2 : 1][(F64 && TMA) ? 128 : 1];
     const uint32_t total_tasks = win_base[w1];            // this launch covers the tasks of windows [w0, w1)
     const uint32_t slot = blockIdx.x * 128u + threadIdx.x;
     if (slot >= total_tasks) return;
@@ -406,10 +413,8 @@ k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict_
     ge_p3 acc;
     if (F64) {
         // FP64-pipe field (fe64.cuh): 1.65x the multiplication rate of the IMAD.WIDE form
-        // The gather of the NEXT point (128-bit cp.async into this thread's shared-memory slot, two
-        // slots per thread) is in flight while the current addition runs, so the HBM/L2 latency of the
-        // random gathers is off the dependent path.
-        constexpr int NQ = KIND == PK_NIELS ? 6 : 8;            // 16-byte pieces per point
+        // The gather of the NEXT point (into this thread's shared-memory slot, two slots per thread) is in flight
+        // while the current addition runs, so the HBM/L2 latency of the random gathers is off the dependent path.
         ge64_p3 acc64;
         if (fold_old) {
             ge_p3 old; load_p3(old, buckets + t);
@@ -418,33 +423,65 @@ k_bucket_accumulate(const void *__restrict__ points, const uint32_t *__restrict_
             ge64_identity(acc64);
         }
         uint32_t e_next = len ? idx[0] : 0;
+        if (TMA) {
+            const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0][threadIdx.x]);
+            const uint32_t bar1 = (uint32_t)__cvta_generic_to_shared(&s_bar[1][threadIdx.x]);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
         auto prefetch = [&](uint32_t e, int buf) {
             const uint32_t pi = e & 0x7fffffffu;
             const char *src = reinterpret_cast<const char *>(points) + (size_t)pi * (NQ * 16);
+            if (TMA) {
+                const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[buf][threadIdx.x]);
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_bulk[buf][threadIdx.x][0]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(NQ * 16) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(src), "r"(NQ * 16), "r"(bar) : "memory");
+            } else {
 #pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_pts[buf][q][threadIdx.x]);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 16 * q) : "memory");
+                for (int q = 0; q < NQ; q++) {
+                    uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_pts[buf][q][threadIdx.x]);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 16 * q) : "memory");
+                }
             }
         };
         if (len) prefetch(e_next, 0);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (!TMA) asm volatile("cp.async.commit_group;" ::: "memory");
         for (uint32_t k = 0; k < len; k++) {
             const uint32_t e = e_next, neg = e >> 31;
             const int buf = k & 1;
             if (k + 1 < len) { e_next = idx[k + 1]; prefetch(e_next, buf ^ 1); }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-            if (KIND == PK_NIELS) {
+            uint32_t words[NQ * 4];
+            if (TMA) {
+                const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[buf][threadIdx.x]);
+                const uint32_t parity = (k >> 1) & 1u;
+                uint32_t done;
+                do {
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                } while (!done);
+                const uint4 *sp = reinterpret_cast<const uint4 *>(&s_bulk[buf][threadIdx.x][0]);
+#pragma unroll
+                for (int q = 0; q < NQ; q++) { uint4 v = sp[q]; words[4 * q] = v.x; words[4 * q + 1] = v.y; words[4 * q + 2] = v.z; words[4 * q + 3] = v.w; }
+            } else {
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+#pragma unroll
+                for (int q = 0; q < NQ; q++) { uint4 v = s_pts[buf][q][threadIdx.x]; words[4 * q] = v.x; words[4 * q + 1] = v.y; words[4 * q + 2] = v.z; words[4 * q + 3] = v.w; }
+            }
+            if constexpr (KIND == PK_NIELS) {
                 ge_niels_packed pk;
 #pragma unroll
-                for (int q = 0; q < 6; q++) { uint4 v = s_pts[buf][q][threadIdx.x]; pk.w[4 * q] = v.x; pk.w[4 * q + 1] = v.y; pk.w[4 * q + 2] = v.z; pk.w[4 * q + 3] = v.w; }
+                for (int q = 0; q < 24; q++) pk.w[q] = words[q];
                 ge64_niels nl; ge64_niels_unpack(nl, pk);
                 ge64_madd(acc64, acc64, nl, neg);
             } else {
                 ge_pniels_packed pk;
 #pragma unroll
-                for (int q = 0; q < 8; q++) { uint4 v = s_pts[buf][q][threadIdx.x]; pk.w[4 * q] = v.x; pk.w[4 * q + 1] = v.y; pk.w[4 * q + 2] = v.z; pk.w[4 * q + 3] = v.w; }
+                for (int q = 0; q < 32; q++) pk.w[q] = words[q];
                 ge64_pniels pn; ge64_pniels_unpack(pn, pk);
                 ge64_padd(acc64, acc64, pn, neg);
             }
@@ -759,9 +796,10 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
     {
         const unsigned grid = cdiv(max_tasks, 128);
         const int f = first ? 1 : 0;
-#define LAUNCH_ACC(KIND_, F64_) k_bucket_accumulate<KIND_, F64_><<<grid, 128, 0, st>>>(d_points, sorted, counts, offsets, ntasks, tasks, order, win_base, 0, nwin, n, nb, task_len, buckets, task_sums, f)
-        if (point_kind == PK_NIELS) { if (ctx->opt_field_f64) LAUNCH_ACC(PK_NIELS, 1); else LAUNCH_ACC(PK_NIELS, 0); }
-        else { if (ctx->opt_field_f64) LAUNCH_ACC(PK_PNIELS, 1); else LAUNCH_ACC(PK_PNIELS, 0); }
+#define LAUNCH_ACC(KIND_, F64_, TMA_) k_bucket_accumulate<KIND_, F64_, TMA_><<<grid, 128, 0, st>>>(d_points, sorted, counts, offsets, ntasks, tasks, order, win_base, 0, nwin, n, nb, task_len, buckets, task_sums, f)
+        const bool tma = ctx->opt_field_f64 && ctx->opt_acc_tma;
+        if (point_kind == PK_NIELS) { if (tma) LAUNCH_ACC(PK_NIELS, 1, 1); else if (ctx->opt_field_f64) LAUNCH_ACC(PK_NIELS, 1, 0); else LAUNCH_ACC(PK_NIELS, 0, 0); }
+        else { if (tma) LAUNCH_ACC(PK_PNIELS, 1, 1); else if (ctx->opt_field_f64) LAUNCH_ACC(PK_PNIELS, 1, 0); else LAUNCH_ACC(PK_PNIELS, 0, 0); }
 #undef LAUNCH_ACC
         k_heavy_fixup<<<ctx->sm_count * 4, 128, 0, st>>>(heavy, ntasks, task_off, win_base, nb, 0u, (uint32_t)nwin, task_sums, buckets, f);
         ctx->launches += 2;

@@ -49,6 +49,15 @@ def load_library():
     lib.dalek_b200_msm_partial_bytes.restype = sz
     lib.dalek_b200_stream.argtypes = [vp]
     lib.dalek_b200_stream.restype = vp
+    lib.dalek_b200_init_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    lib.dalek_b200_destroy_multi.argtypes = [vp]
+    lib.dalek_b200_destroy_multi.restype = None
+    lib.dalek_b200_multi_device_count.argtypes = [vp]
+    lib.dalek_b200_multi_ctx.argtypes = [vp, C.c_int]
+    lib.dalek_b200_multi_ctx.restype = vp
+    lib.dalek_b200_multi_last_error.argtypes = [vp]
+    lib.dalek_b200_multi_last_error.restype = C.c_char_p
+    lib.dalek_b200_edwards_vartime_msm_multi.argtypes = [vp, vp, vp, C.c_int, sz, vp, vp]
     lib.dalek_b200_ristretto_double_base_batch.argtypes = [vp, vp, vp, vp, vp, sz, vp]
     lib.dalek_b200_ristretto_vartime_msm.argtypes = [vp, vp, vp, sz, vp]
     lib.ed25519_b200_verify_batch.argtypes = [vp, vp, vp, vp, vp, sz]
@@ -321,6 +330,55 @@ class Engine:
         self._check(self.lib.ed25519_b200_sign_batch_flat(self.h, _ptr(seeds), _ptr(msgs_flat), _ptr(offsets), n,
                                                           C.addressof(pks), C.addressof(sigs)))
         return bytes(pks)[:32 * n], bytes(sigs)[:64 * n]
+
+
+class MultiEngine:
+    """One MSM over several GPUs of this node from a single process (dalek_b200_init_multi): contiguous shards, peer
+    copies of the window-accumulator records to the first device, combine there."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.dalek_b200_init_multi(devs, len(devices), C.byref(h))
+        if rc != 0:
+            raise EngineError("dalek_b200_init_multi(%r) failed with %d (the engine has no CPU fallback)" % (list(devices), rc))
+        self.h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dalek_b200_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name, value):
+        for i in range(len(self.devices)):
+            rc = self.lib.dalek_b200_set_option(self.lib.dalek_b200_multi_ctx(self.h, i), name.encode(), int(value))
+            if rc:
+                raise EngineError("set_option(%s) failed" % name)
+
+    def last_call_ms(self):
+        ms = C.c_float()
+        self.lib.dalek_b200_last_call_ms(self.lib.dalek_b200_multi_ctx(self.h, 0), C.byref(ms))
+        return float(ms.value)
+
+    def edwards_vartime_msm(self, scalars, points, n, point_fmt=POINTS_COMPRESSED, want_limbs=False):
+        """(rc, compressed32, limbs20 or None) like Engine.edwards_vartime_msm, host buffers."""
+        out = (C.c_uint8 * 32)()
+        limbs = (C.c_uint64 * 20)() if want_limbs else None
+        keep = (scalars, points)
+        rc = self.lib.dalek_b200_edwards_vartime_msm_multi(self.h, _ptr(scalars), _ptr(points), point_fmt, n, C.addressof(out),
+                                                           C.addressof(limbs) if want_limbs else None)
+        del keep
+        if rc < 0:
+            raise EngineError("engine error %d: %s" % (rc, self.lib.dalek_b200_multi_last_error(self.h).decode()))
+        return rc, bytes(out), (list(limbs) if want_limbs else None)
 
 
 _default = None

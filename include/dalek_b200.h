@@ -150,6 +150,24 @@ int dalek_b200_edwards_msm_combine_dev(dalek_b200_ctx *ctx, const void *d_record
 /* The context's main CUDA stream (a cudaStream_t) for callers that order their own work with the engine's. */
 void *dalek_b200_stream(dalek_b200_ctx *ctx);
 
+/* -------- one MSM over several GPUs from a single process ---------------------
+ * dalek_b200_init_multi creates one engine context per listed CUDA device (distinct sm_100 devices of one node)
+ * and enables peer access to the first one.  ..._vartime_msm_multi is VartimeMultiscalarMul::optional_multiscalar_mul
+ * (C/traits.rs:196-262, same conventions as dalek_b200_edwards_vartime_msm, host buffers) with the pair range cut
+ * into contiguous shards, one per device: every device reduces its shard to window accumulators, the ~2.7 KB records
+ * are written into the first device's memory by peer copies over NVLink, and the first device combines them
+ * (pippenger.rs:146-159).  Inputs of fewer than 2^14 pairs per device run on the first device alone. */
+typedef struct dalek_b200_multi dalek_b200_multi;
+int dalek_b200_init_multi(const int *devices, int ndev, dalek_b200_multi **out);
+void dalek_b200_destroy_multi(dalek_b200_multi *m);
+int dalek_b200_multi_device_count(const dalek_b200_multi *m);
+/* The context of device i (e.g. to set options, or to run replicas of verify_batch on every GPU). */
+dalek_b200_ctx *dalek_b200_multi_ctx(dalek_b200_multi *m, int i);
+const char *dalek_b200_multi_last_error(const dalek_b200_multi *m);
+int dalek_b200_edwards_vartime_msm_multi(dalek_b200_multi *m, const uint8_t *scalars, const void *points,
+                                         int point_fmt, size_t n, uint8_t out_compressed[32],
+                                         uint64_t out_limbs[20]);
+
 /* -------- VartimePrecomputedMultiscalarMul ---------------------------------
  * C/traits.rs:290-406; VartimeEdwardsPrecomputation C/edwards.rs:1038-1076, VartimeRistrettoPrecomputation
  * C/ristretto.rs:1004-1049 (serial backend: precomputed_straus.rs:33-127).  The static points are decoded
