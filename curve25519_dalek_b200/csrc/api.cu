@@ -76,6 +76,7 @@ int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value)
     if (!strcmp(name, "double_base_comb")) { ctx->opt_double_base_comb = value ? 1 : 0; return 0; }
     if (!strcmp(name, "dedupe_keys")) { ctx->opt_dedupe_keys = value ? 1 : 0; return 0; }
     if (!strcmp(name, "verify_pieces")) { if (value < 1 || value > 8) return DALEK_E_INVALID_ARG; ctx->opt_verify_pieces = value; return 0; }
+    if (!strcmp(name, "small_straus")) { ctx->opt_small_straus = value ? 1 : 0; return 0; }
     if (!strcmp(name, "acc_tma")) { ctx->opt_acc_tma = value ? 1 : 0; return 0; }
     if (!strcmp(name, "field_f64")) { ctx->opt_field_f64 = value ? 1 : 0; return 0; }
     if (!strcmp(name, "verify_chunk")) { if (value < 0 || value > (1 << 20)) return DALEK_E_INVALID_ARG; ctx->opt_verify_chunk = value; return 0; }
@@ -121,9 +122,14 @@ static int run_msm(dalek_b200_ctx *ctx, const void *scalars, const void *points_
     if ((rc = ws_reserve(ctx, ctx->flags, 64))) return rc;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->flags.p, 0, 64, st));
     const int c = msm_choose_window_bits(ctx, n_window);
+    // the reference's dispatch (edwards.rs:1025-1029): below 190 points vartime Straus -- here three launches
+    // (straus_vt.cu) instead of the ~27 of the bucket pipeline; only for whole MSMs (a shard must yield window sums)
+    const bool straus = d_result && n == n_window && n < STRAUS_VT_THRESHOLD && ctx->opt_small_straus && ctx->opt_field_f64;
     if (on_device) {
         if ((rc = msm_prepare_points(ctx, points_in, point_fmt, n, ctx->points.p, (int *)ctx->flags.p))) return rc;
-        if ((rc = msm_accumulate_chunk(ctx, (const uint32_t *)scalars, ctx->points.p, kind, n, c, true))) return rc;
+        if (straus) {
+            if ((rc = straus_vartime_msm(ctx, (const uint32_t *)scalars, ctx->points.p, kind, n, d_result))) return rc;
+        } else if ((rc = msm_accumulate_chunk(ctx, (const uint32_t *)scalars, ctx->points.p, kind, n, c, true))) return rc;
     } else {
         if ((rc = ws_reserve(ctx, ctx->scalars, std::max<size_t>(1, n) * 32))) return rc;
         if ((rc = ws_reserve(ctx, ctx->points_in, std::max<size_t>(1, n) * pin))) return rc;
@@ -143,10 +149,12 @@ static int run_msm(dalek_b200_ctx *ctx, const void *scalars, const void *points_
             CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_grp[k], 0));
             char *dq = (char *)ctx->points.p + i0 * psz;
             if ((rc = msm_prepare_points(ctx, dp, point_fmt, cnt, dq, (int *)ctx->flags.p))) return rc;
-            if ((rc = msm_accumulate_chunk(ctx, (const uint32_t *)ds, dq, kind, cnt, c, k == 0))) return rc;
+            if (straus) {                                            // K = 1 for small inputs
+                if ((rc = straus_vartime_msm(ctx, (const uint32_t *)ds, dq, kind, cnt, d_result))) return rc;
+            } else if ((rc = msm_accumulate_chunk(ctx, (const uint32_t *)ds, dq, kind, cnt, c, k == 0))) return rc;
         }
     }
-    if ((rc = msm_reduce_finish(ctx, c, d_windows, d_result))) return rc;
+    if (!straus && (rc = msm_reduce_finish(ctx, c, d_windows, d_result))) return rc;
     if (bad_out) CUDA_TRY(ctx, cudaMemcpyAsync(bad_out, ctx->flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     return 0;
 }

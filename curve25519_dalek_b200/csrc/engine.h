@@ -39,6 +39,7 @@ struct dalek_b200_ctx {
     long opt_verify_pieces = 4; // host-buffer verify_batch calls stream the signatures in this many pieces
     long opt_decompress_f64 = 1; // square-root exponentiation of point decompression on the FP64-pipe field
     long opt_acc_tma = 0;       // bucket kernel gathers points with TMA bulk copies + mbarriers instead of cp.async (A/B option)
+    long opt_small_straus = 1;  // fewer than 190 pairs: vartime Straus (3 launches) instead of the bucket pipeline
     long opt_field_f64 = 1;     // bucket kernel on the FP64 pipe (fe64.cuh) instead of IMAD.WIDE (fe.cuh)
     // timing of the dominant kernel in the last call
     float last_kernel_ms = 0.f;
@@ -148,6 +149,11 @@ int msm_partial_enqueue_record(dalek_b200_ctx *ctx, const void *scalars, const v
 // `ranks` records (host or device, rec_bytes apart) -> per-window sums, Horner, encode; blocks for the result.
 int msm_combine_records(dalek_b200_ctx *ctx, const void *records, bool on_device, size_t rec_bytes, int ranks, size_t n_shard,
                         uint8_t out_compressed[32], uint64_t out_limbs[20]);
+
+// ---- variable-time Straus for small inputs (straus_vt.cu): the reference's path below 190 points ----
+#define STRAUS_VT_THRESHOLD 190            // edwards.rs:1025-1029
+int straus_vartime_msm(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n,
+                       MsmResult *d_result);
 
 // ---- constant-time Straus (straus.cu) ----
 int straus_ct_msm(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points_pniels, size_t n,

@@ -105,6 +105,55 @@ def test_msm_skewed_buckets(eng, oracle):
     assert rc == 0 and got == want
 
 
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 17, 64, 65, 150, 189])
+def test_small_msm_straus_path_and_bucket_path_agree(eng, oracle, n):
+    """Below 190 points the engine follows the reference's dispatch (edwards.rs:1025-1029) to vartime Straus
+    (csrc/straus_vt.cu: device non_adjacent_form(5), NafLookupTable5, straus.rs:159-200); the option `small_straus`
+    switches back to the bucket pipeline.  Both must give the oracle's Straus result, for compressed and extended
+    points, edge scalars, small-order points, and scalars with bit 255 set (legal at this boundary)."""
+    scalars, points = gen_case(oracle, n)
+    rnd = random.Random(n)
+    if n >= 9:
+        scalars[7] = (2**256 - 1).to_bytes(32, "little")             # beyond the reference's Scalar invariant
+        scalars[8] = (2**255 + rnd.randrange(2**255)).to_bytes(32, "little")
+    # oracle: the Straus algorithm itself for reference-legal scalars, exact integer arithmetic otherwise
+    legal = all(int.from_bytes(x, "little") < 2**255 for x in scalars)
+    if legal:
+        want = oracle.compress(oracle.msm("straus_vartime", scalars, points))
+        assert want == oracle.compress(oracle.msm("optional", scalars, points))
+    else:
+        acc = oracle.identity()
+        for sc, pt in zip(scalars, points):
+            v = int.from_bytes(sc, "little")
+            lo = oracle.scalarmul((v % 2**252).to_bytes(32, "little"), pt)             # v = lo + 2^252 hi
+            hi = oracle.mul_by_pow_2(oracle.scalarmul((v >> 252).to_bytes(32, "little"), pt), 252)
+            acc = oracle.add(acc, oracle.add(lo, hi))
+        want = oracle.compress(acc)
+    sb = b"".join(scalars)
+    comp = b"".join(oracle.compress(p) for p in points)
+    ext = (C.c_uint64 * (20 * n))()
+    for i, pt in enumerate(points):
+        q = oracle.sub(oracle.add(oracle.double(pt), pt), oracle.double(pt))           # Z != 1
+        for k, v in enumerate(oracle.p3_limbs(q)):
+            ext[20 * i + k] = v
+    for straus in (1, 0):
+        eng.set_option("small_straus", straus)
+        try:
+            l0 = eng.launch_count()
+            rc, got, _ = eng.edwards_vartime_msm(sb, comp, n, point_fmt=0)
+            launches = eng.launch_count() - l0
+            assert rc == 0 and got == want, straus
+            assert (launches <= 5) == bool(straus)                   # 4 launches against ~27
+            rc, got, _ = eng.edwards_vartime_msm(sb, ext, n, point_fmt=1)
+            assert rc == 0 and got == want, straus
+        finally:
+            eng.set_option("small_straus", 1)
+    # an undecodable point still gives None on the Straus path
+    bad = bytearray(comp); bad[32 * (n - 1):32 * n] = (2).to_bytes(32, "little")
+    rc, _, _ = eng.edwards_vartime_msm(sb, bytes(bad), n, point_fmt=0)
+    assert rc == 1
+
+
 def test_msm_sharded_partial_combine(eng, oracle):
     """contiguous shards -> window accumulators -> combine == single MSM.  The window width comes from
     the SHARD size (the work one GPU does), identical on every rank."""
