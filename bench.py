@@ -37,6 +37,7 @@ L_ORDER = 2**252 + 27742317777372353535851937790883648493
 SEED = 0xDA1EC00000000001
 IMAD_WIDE_PEAK_PER_S = 8.96e12      # measured on this pool's B200, profiles/microbench_r1.json
 FIELD_MUL_PEAK_PER_S = 119e9        # field multiplications/s of the FP64-pipe field in isolation, profiles/microbench_f64_r1.json
+FIELD_SQ_PEAK_PER_S = 142e9          # field squarings/s of the FP64-pipe field in isolation (fe64_sq), profiles/microbench_f64_r1.json
 FIELD_MUL_PEAK_INT_PER_S = 71e9     # same for the IMAD.WIDE field (fe.cuh), profiles/microbench_r1.json
 
 
@@ -373,6 +374,12 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
     torch.cuda.synchronize()
 
     each_res = np.zeros(n, dtype=np.uint8) if each else None
+    # One call over n = 2^22 signatures: the reference's single Merlin transcript is a strictly sequential sponge of
+    # 1.73 Keccak permutations per signature (seconds for 2^22, on any hardware), so this leg opts into one transcript per
+    # `transcript_chunk` signatures (verdict-equivalent on inputs without small-order components).  The
+    # batches_of_256 leg and every call with the default options use exactly the reference's transcripts.
+    transcript_chunk = 0 if (each or batch_size) else args.transcript_chunk
+    eng.set_option("verify_chunk", transcript_chunk)
 
     def step(host=False):
         b = h if host else d
@@ -401,11 +408,17 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
 
     # negative control: one flipped message bit must give Verify (1)
     d[0][59 * 777 + 3] ^= 1
-    rc = eng.verify_batch_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, device_ptrs=True)
     if each:
         rc_e, res_e = eng.verify_each_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), 1024, device_ptrs=True)
         if rc_e != 1 or [i for i, r in enumerate(res_e) if r] != [777]:
             raise SystemExit("bench: verify_each did not single out the corrupted signature")
+        rc = 1
+    elif batch_size:
+        rc, verd = eng.verify_batches_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, batch_size, device_ptrs=True)
+        if [k for k, v in enumerate(verd) if v] != [777 // batch_size]:
+            raise SystemExit("bench: verify_batches did not single out the corrupted batch")
+    else:
+        rc = eng.verify_batch_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, device_ptrs=True)
     d[0][59 * 777 + 3] ^= 1
     if rc != 1:
         raise SystemExit("bench: corrupted batch was not rejected (rc=%d)" % rc)
@@ -418,11 +431,13 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
         sampler.start()
     l0 = eng.launch_count()
     t0 = time.perf_counter()
-    call_ms, e2e_call_ms = [], []
+    call_ms, e2e_call_ms, prep_ms = [], [], []
     for _ in range(steps):
         step()
         kernel_ms.append(eng.last_kernel_ms()[0])
         call_ms.append(eng.last_call_ms())
+        if not each and not batch_size:
+            prep_ms.append(eng.last_stage_ms("decompress_R"))
     barrier()
     t1 = time.perf_counter()
     launches = eng.launch_count() - l0
@@ -443,17 +458,42 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     et = float(et.item())
+    eng.set_option("verify_chunk", 0)
     if rank != 0:
         return None
     peaks, how = measured_peaks()
     kms = statistics.mean(kernel_ms)
     achieved = n * 155 / (el / steps) / 1e9
+    # dominant kernel of verify_batch: the decompression of the n R points (252 squarings + 13 multiplications each, on the
+    # FP64-pipe field), timed with CUDA events on its stream while the hashing / transcript kernels share the SMs
+    pms = statistics.mean(prep_ms) if prep_ms and min(prep_ms) > 0 else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("k_prep_R_verify_2p22_bytes")
+    dominant = None
+    if pms:
+        sq = n * 265.0
+        dominant = {"bound": "hbm", "kernel": "k_prep_R (R decompression)", "kernel_ms": pms,
+                    "achieved": n * 155 / (pms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": n * 155 / (pms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic,
+                    "algorithmic_bytes_per_launch": n * 155, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
+                    "note": "arithmetic-bound: see field_ops",
+                    "field_ops": {"achieved": sq / (pms * 1e-3) / 1e9, "peak": FIELD_SQ_PEAK_PER_S / 1e9, "unit": "G field squarings/s",
+                                  "frac": sq / (pms * 1e-3) / FIELD_SQ_PEAK_PER_S,
+                                  "algorithmic_field_ops_per_launch": sq,
+                                  "peak_source": "register-resident squaring chain of the same FP64-pipe field code (profiles/microbench_f64_r1.json); "
+                                                 "252 squarings + 13 multiplications per point (field.rs:297-306, :320-366), the kernel runs "
+                                                 "concurrently with the SHA-512 and Merlin kernels of the same call"}}
     return {
         "metric": "Ed25519 verify_batch signatures/sec", "value": n * world * steps / el, "unit": "sigs/s",
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": el / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "exact integers: f64 limbs (radix 2^51, FP64 pipe) in the bucket kernel, u32 limbs (radix 2^25.5) elsewhere", "data": "synthetic: 59-byte messages, %d distinct keys, signatures made on the GPU (RFC 8032)" % min(nkeys, n),
         "config": {"workload": "ed25519_verify_batch", "signatures_per_gpu": n, "message_bytes": 59, "distinct_keys": min(nkeys, n),
-                   "verify_chunk": 64, "keys": "32-byte encodings, decompressed inside the call",
+                   "transcript": ("one Merlin transcript per %d signatures (option verify_chunk, opt-in; default = the reference's single transcript)" % transcript_chunk)
+                                 if transcript_chunk else "the reference's transcripts (one per batch)",
+                   "keys": "32-byte encodings, decompressed inside the call",
                    "batch_size": batch_size or None,
                    "timing": "value / ms_per_step: K blocking C-ABI calls bracketed by barrier + device sync, max over ranks; "
                              "device_ms_per_step: CUDA events on the engine's stream around each call (rank 0)",
@@ -463,11 +503,32 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
         "e2e": {"value": n * world * steps / et, "unit": "sigs/s", "h2d_bytes_per_step": n * 155 + (n + 1) * 8,
                 "d2h_bytes_per_step": n if each else (4 * ((n + batch_size - 1) // batch_size) if batch_size else 192)},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "whole call (155 B per signature)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": how,
-                     "bucket_kernel_ms": kms, "note": "integer-multiply bound (decompression + MSM)"},
+        "roofline": dominant or {"bound": "hbm", "kernel": "whole call (155 B per signature)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": how,
+                                 "note": "integer-multiply bound (decompression + MSM)"},
+        "roofline_whole_call": {"achieved": achieved, "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "bucket_kernel_ms": kms},
         "clocks": clocks,
     }
+
+
+def run_verify_exact_once(eng, args, n=1 << 18):
+    """One verify_batch call over n signatures with the DEFAULT options: the reference's single Merlin transcript
+    (batch.rs:168-222), a sequential sponge of 1.73 Keccak-f[1600] permutations per signature on one GPU thread."""
+    import numpy as np
+    import torch
+    flat, offs, sigs, pks = build_verify_inputs(eng, n, nkeys=1024)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d = [torch.from_numpy(x if x.dtype == np.uint8 else x.view(np.int64)).to(dev) for x in (flat, offs, sigs, pks)]
+    eng.set_option("verify_chunk", 0)
+    t0 = time.perf_counter()
+    rc = eng.verify_batch_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, device_ptrs=True, msgs_bytes=n * 59)
+    dt = time.perf_counter() - t0
+    if rc != 0:
+        raise SystemExit("bench: verify_batch (single transcript) returned %d on valid signatures" % rc)
+    return {"signatures": n, "seconds": dt, "value": n / dt, "unit": "sigs/s",
+            "note": "ONE call, ONE transcript over all signatures (exactly the reference's z_i): bound by the sequential sponge, "
+                    "not by the GPU's arithmetic; callers with large inputs use verify_batches (one reference transcript per batch) "
+                    "or opt into verify_chunk"}
 
 
 def run_precomputed(eng, wl, steps=10):
@@ -524,12 +585,13 @@ def run_codecs(eng, wl, steps=5):
     return out
 
 
-def run_double_base(eng, n=1 << 20, steps=3):
+def run_double_base(eng, n=1 << 20, steps=3, cpu_threads=1):
     """BASELINE configs[4]: RistrettoPoint::multiscalar_mul([a_i, b_i], [G, H]) for 2^20 pairs (constant-time
-    contract), host buffers in, compressed points out (64 B in + 32 B out per pair)."""
+    contract), host buffers in, compressed points out (64 B in + 32 B out per pair).  A 4096-pair sample of the output is
+    compared with the oracle's constant-time Straus (straus.rs:103-144 -> ristretto.rs:500-533); the same oracle run on
+    one host thread is the cpu_baseline."""
     import numpy as np
     a, b = fast_scalars(n, seed=31), fast_scalars(n, seed=32)
-    _, Gc = eng.mul_base_batch(np.frombuffer((1).to_bytes(32, "little"), dtype=np.uint8).copy(), 1)
     # Ristretto basepoint encoding (curve25519-dalek/src/constants.rs:57-60) and H = h*G via the engine itself
     G = bytes.fromhex("e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76")
     h = np.frombuffer(hashlib.sha512(b"dalek-b200/H").digest()[:32], dtype=np.uint8).copy(); h[31] &= 0x0F
@@ -544,10 +606,97 @@ def run_double_base(eng, n=1 << 20, steps=3):
         rc, _ = eng.ristretto_double_base_batch(ha, hb, G, H, n, out=hout)
     dt = (time.perf_counter() - t0) / steps
     assert rc == 0
+    out = hout.numpy().reshape(n, 32)
+    # oracle parity on a sample spread over the batch (first, last and strided pairs), timed as the CPU baseline
+    ns = 4096
+    idx = np.unique(np.concatenate([np.arange(0, 1024), np.arange(n - 1024, n), np.linspace(1024, n - 1025, 2048).astype(np.int64)]))[:ns]
+    pool = CpuPool(cpu_threads)
+    cdt, want = pool.double_base(np.ascontiguousarray(a[idx]), np.ascontiguousarray(b[idx]), G, H, len(idx))
+    pool.close()
+    if not np.array_equal(want, out[idx]):
+        raise SystemExit("bench: double-base batch differs from the oracle on the %d-pair sample" % len(idx))
     return {"metric": "Ristretto double-base (aG+bH) pairs/sec, pinned host buffers in and out", "value": n / dt, "unit": "pairs/s",
             "ms_per_step": dt * 1e3, "device_span_ms": eng.last_kernel_ms()[0], "pairs": n,
             "h2d_bytes_per_step": 64 * n, "d2h_bytes_per_step": 32 * n,
-            "checksum": hashlib.sha256(hout.numpy().tobytes()).hexdigest()[:16]}
+            "parity": "%d-pair sample (first 1024, last 1024, 2048 strided) byte-equal to the oracle's constant-time Straus + Ristretto encoding" % len(idx),
+            "checksum": hashlib.sha256(hout.numpy().tobytes()).hexdigest()[:16],
+            "cpu_baseline": {"value": len(idx) / cdt, "unit": "pairs/s", "cores": cpu_threads, "kind": "port",
+                             "sample": "oracle RistrettoPoint::multiscalar_mul([a,b],[G,H]) + compress on the %d-pair parity sample (%.1f s)" % (len(idx), cdt)}}
+
+
+def run_msm_compressed(eng, wl, steps=10):
+    """the compressed-input variant of config 2 -- 64 B per pair (32 B scalar + 32 B CompressedEdwardsY), the
+    points are decompressed inside the call (edwards.rs:211-257).  Device-resident and end to end from pinned host memory."""
+    import torch
+    n = wl.n
+    enc = torch.empty(32 * n, dtype=torch.uint8).pin_memory()
+    assert eng.lib.dalek_b200_edwards_compress_batch(eng.h, wl.h_points.data_ptr(), n, enc.data_ptr()) == 0
+    d_enc = enc.cuda()
+    want = wl.step_device_single()
+    res = {}
+    for name, sp, pp, dev_ptrs in (("device_resident", wl.d_scalars, d_enc, True), ("e2e", wl.h_scalars, enc, False)):
+        for _ in range(3):
+            rc, got, _ = eng.edwards_vartime_msm(sp.data_ptr(), pp.data_ptr(), n, point_fmt=0, device_ptrs=dev_ptrs)
+        assert rc == 0 and got == want, "compressed-input MSM differs from the extended-input result"
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(steps):
+            eng.edwards_vartime_msm(sp.data_ptr(), pp.data_ptr(), n, point_fmt=0, device_ptrs=dev_ptrs)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        res[name] = {"value": n / dt, "unit": "points/s", "ms_per_step": dt * 1e3}
+    res["e2e"].update({"h2d_bytes_per_step": 64 * n, "d2h_bytes_per_step": 192})
+    res.update({"metric": "Pippenger MSM points/sec, compressed points (64 B per pair), decompression inside the call", "pairs": n,
+                "matches_extended_input_result": True})
+    return res
+
+
+def run_small_latency(eng, sizes=(1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024), reps=30):
+    """BASELINE configs[0] and the reference's own bench sizes (dalek_benchmarks.rs:16, :145-189): latency of ONE
+    vartime_multiscalar_mul call on host buffers (in-memory EdwardsPoints, 160 B each), GPU engine against the oracle on one
+    host thread, results compared byte for byte.  Below 190 points both GPU paths are timed (vartime Straus / bucket pipeline)."""
+    import numpy as np
+    nmax = max(sizes)
+    t = fast_scalars(nmax, seed=501)
+    sc = fast_scalars(nmax, seed=502)
+    limbs, _ = eng.mul_base_batch(t, nmax, want_compressed=False)
+    pts = np.frombuffer(limbs, dtype=np.uint64).reshape(nmax, 20).copy()
+    pool = CpuPool(1)
+    rows = []
+
+    def gpu_us(n):
+        for _ in range(3):
+            rc, got, _ = eng.edwards_vartime_msm(sc, pts, n, point_fmt=1)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            eng.edwards_vartime_msm(sc, pts, n, point_fmt=1)
+            ts.append(time.perf_counter() - t0)
+        return statistics.median(ts) * 1e6, got
+
+    for n in sizes:
+        cpu = []
+        for _ in range(3):
+            dt, want = pool.msm(sc, pts, n, slice_pairs=n)
+            cpu.append(dt)
+        row = {"n": n, "cpu_us": statistics.median(cpu) * 1e6}
+        us, got = gpu_us(n)
+        if got != want:
+            raise SystemExit("bench: small MSM (n=%d) differs from the oracle" % n)
+        row["gpu_us"] = us
+        if n < 190:
+            eng.set_option("small_straus", 0)
+            row["gpu_bucket_pipeline_us"], got2 = gpu_us(n)
+            eng.set_option("small_straus", 1)
+            if got2 != want:
+                raise SystemExit("bench: small MSM through the bucket pipeline (n=%d) differs from the oracle" % n)
+        rows.append(row)
+    pool.close()
+    faster = [r["n"] for r in rows if r["gpu_us"] < r["cpu_us"]]
+    return {"metric": "latency of one EdwardsPoint::vartime_multiscalar_mul call, host buffers (160-byte points), microseconds",
+            "sizes": rows, "gpu_faster_from_n": min(faster) if faster else None,
+            "cpu": "oracle (reference algorithm: Straus below 190 points, Pippenger above), 1 host thread, median of 3",
+            "gpu": "blocking C-ABI call incl. copies, median of %d; n < 190: vartime Straus kernels (4 launches), else the bucket pipeline" % reps,
+            "config1_n256": next((r for r in rows if r["n"] == 256), None)}
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline (oracle)
@@ -720,6 +869,8 @@ def main():
     ap.add_argument("--workload", default="msm", choices=["msm", "verify"])
     ap.add_argument("--pairs-per-gpu", type=int, default=0)
     ap.add_argument("--sigs-per-gpu", type=int, default=0)
+    ap.add_argument("--transcript-chunk", type=int, default=64, help="signatures per Merlin transcript in the single-call verify_batch leg (0 = the reference's single transcript)")
+    ap.add_argument("--exact-transcript-leg", type=int, default=1, help="also time ONE 2^18-signature verify_batch call with the reference's single transcript")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary verify_batch / cpu_baseline legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -746,6 +897,8 @@ def main():
                 line["verify_batch"] = {k: v[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "e2e", "config", "gpu_launches", "roofline")}
         if not args.no_extras and world == 1:
             line["msm_2p21_pairs"] = run_msm_like_for_like(eng, 1 << 21, min(args.steps, 20))
+            line["msm_compressed_input"] = run_msm_compressed(eng, wl)
+            line["small_msm_latency"] = run_small_latency(eng)
             line["msm_precomputed"] = run_precomputed(eng, wl)
             line["codecs"] = run_codecs(eng, wl)
             v = run_verify(args, rank, world, local, eng=eng, steps=min(args.steps, 5), warmup=3)
@@ -756,9 +909,19 @@ def main():
             # the same signatures as 2^14 independent batches of 256 (per-batch verdicts, one reference transcript each)
             v3 = run_verify(args, rank, world, local, eng=eng, steps=3, warmup=3, batch_size=256)
             line["verify_batch"]["batches_of_256"] = {k: v3[k] for k in ("value", "unit", "ms_per_step", "e2e")}
+            # the single-call leg again with the reference's ONE transcript over all 2^22 signatures (the default of the API):
+            # a strictly sequential sponge, one GPU thread -- timed once
+            if args.exact_transcript_leg:
+                line["verify_batch"]["single_reference_transcript"] = run_verify_exact_once(eng, args)
             # one verdict per signature (VerifyingKey::verify semantics: R' recomputed and compared as bytes)
             v4 = run_verify(args, rank, world, local, eng=eng, steps=2, warmup=1, each=True)
             line["verify_each"] = {k: v4[k] for k in ("value", "unit", "ms_per_step", "e2e")}
+            pool = CpuPool(1)
+            m_, s_, k_ = pool.verify_inputs(2048)
+            cdt = pool.verify_each(m_, s_, k_, 2048)
+            pool.close()
+            line["verify_each"]["cpu_baseline"] = {"value": 2048 / cdt, "unit": "sigs/s", "cores": 1, "kind": "port",
+                                                   "sample": "2048 oracle VerifyingKey::verify calls, 1 thread (%.1f s)" % cdt}
             line["ristretto_double_base"] = run_double_base(eng)
     if rank == 0 and world == 1 and not args.no_extras:
         threads = 1

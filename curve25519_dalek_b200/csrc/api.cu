@@ -38,7 +38,8 @@ int dalek_b200_init(int device, dalek_b200_ctx **out)
         return DALEK_E_CUDA;
     }
     for (int i = 0; i < 8; i++)
-        if (cudaEventCreateWithFlags(&ctx->ev_grp[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return DALEK_E_CUDA; }
+        if (cudaEventCreateWithFlags(&ctx->ev_grp[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&ctx->ev_prep[i][0]) != cudaSuccess ||
+            cudaEventCreate(&ctx->ev_prep[i][1]) != cudaSuccess) { delete ctx; return DALEK_E_CUDA; }
     *out = ctx;
     return DALEK_OK;
 }
@@ -58,7 +59,7 @@ void dalek_b200_destroy(dalek_b200_ctx *ctx)
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     cudaEventDestroy(ctx->ev_join2); cudaEventDestroy(ctx->ev_call0); cudaEventDestroy(ctx->ev_call1);
-    for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev_grp[i]);
+    for (int i = 0; i < 8; i++) { cudaEventDestroy(ctx->ev_grp[i]); cudaEventDestroy(ctx->ev_prep[i][0]); cudaEventDestroy(ctx->ev_prep[i][1]); }
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2); cudaStreamDestroy(ctx->stream_copy); cudaStreamDestroy(ctx->stream3);
     delete ctx;
 }
@@ -91,6 +92,14 @@ int dalek_b200_last_kernel_ms(const dalek_b200_ctx *ctx, float *ms, int *launche
     if (ms) *ms = ctx->last_kernel_ms;
     if (launches) *launches = ctx->last_kernel_launches;
     return 0;
+}
+
+int dalek_b200_last_stage_ms(const dalek_b200_ctx *ctx, const char *stage, float *ms)
+{
+    if (!ctx || !stage || !ms) return DALEK_E_INVALID_ARG;
+    if (!strcmp(stage, "bucket_accumulate")) { *ms = ctx->last_kernel_ms; return 0; }
+    if (!strcmp(stage, "decompress_R")) { *ms = ctx->last_prep_ms; return 0; }
+    return DALEK_E_INVALID_ARG;
 }
 
 int dalek_b200_last_call_ms(const dalek_b200_ctx *ctx, float *ms)

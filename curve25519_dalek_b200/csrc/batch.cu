@@ -396,11 +396,13 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
         }
     }
     ge_niels_packed *points_A = b.points + 1;
+    if (piece < 8) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev_prep[piece][0], st2)); ctx->prep_pieces = piece + 1; }
     if (ctx->opt_decompress_f64)
         k_prep_R<1><<<cdiv(cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, cnt, b.points + 1 + n + i0, i0 == 0 ? b.points : nullptr, b.flags, b.bad_r + i0);
     else
         k_prep_R<0><<<cdiv(cnt + 1, 128), 128, 0, st2>>>(d_sigs + 16 * i0, cnt, b.points + 1 + n + i0, i0 == 0 ? b.points : nullptr, b.flags, b.bad_r + i0);
     ctx->launches++;
+    if (piece < 8) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_prep[piece][1], st2));
     trace_mark(ctx, "prep_R done (decompress stream)", st2);
     if (ctx->opt_dedupe_keys) {
         // keys first seen in this piece are uniq[counters[piece] .. counters[1 + piece])  (counters[15] = 0 for piece 0)
@@ -533,6 +535,9 @@ static int verify_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, int p
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
+    ctx->last_prep_ms = 0.f;
+    for (int k = 0; k < ctx->prep_pieces; k++)
+        if (cudaEventElapsedTime(&ms, ctx->ev_prep[k][0], ctx->ev_prep[k][1]) == cudaSuccess) ctx->last_prep_ms += ms;
     trace_dump(ctx);
     // error precedence follows the reference: VerifyingKey::from_bytes happens before verify_batch
     // can be called (PointDecompression); then s canonicity (batch.rs:208-211); then R / equation.

@@ -25,6 +25,9 @@ struct dalek_b200_ctx {
     cudaStream_t stream3 = nullptr;      // second hashing/transcript chain (odd verify pieces)
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;   // device span of the last hot-path call (CallTimer)
+    cudaEvent_t ev_prep[8][2] = {};      // around the R-decompression kernel of each verify_batch piece (stream2)
+    int prep_pieces = 0;
+    float last_prep_ms = 0.f;            // their sum in the last verify_batch call
     cudaEvent_t ev_grp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // one per input piece
     std::string last_error;
     uint64_t launches = 0;

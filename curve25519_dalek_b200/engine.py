@@ -36,6 +36,7 @@ def load_library():
     lib.dalek_b200_launch_count.restype = C.c_uint64
     lib.dalek_b200_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.dalek_b200_last_call_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.dalek_b200_last_stage_ms.argtypes = [vp, C.c_char_p, C.POINTER(C.c_float)]
     for name in ("dalek_b200_edwards_vartime_msm", "dalek_b200_edwards_ct_msm", "dalek_b200_edwards_vartime_msm_dev"):
         getattr(lib, name).argtypes = [vp, vp, vp, C.c_int, sz, vp, vp]
     lib.dalek_b200_msm_window_count.argtypes = [vp, sz]
@@ -159,6 +160,12 @@ class Engine:
         """Device time (CUDA events on the engine's stream) of the last MSM / verify_batch call, in ms."""
         ms = C.c_float()
         self.lib.dalek_b200_last_call_ms(self.h, C.byref(ms))
+        return float(ms.value)
+
+    def last_stage_ms(self, stage):
+        """Device time of a named stage of the last call: 'bucket_accumulate' or 'decompress_R'."""
+        ms = C.c_float()
+        self._check(self.lib.dalek_b200_last_stage_ms(self.h, stage.encode(), C.byref(ms)))
         return float(ms.value)
 
     def last_kernel_ms(self):

@@ -73,6 +73,9 @@ uint64_t dalek_b200_launch_count(const dalek_b200_ctx *ctx);
 /* Milliseconds (CUDA events on the context's stream) spent in the dominant kernel of the last
  * call (bucket accumulation for MSM calls), and that kernel's launch count in the last call. */
 int dalek_b200_last_kernel_ms(const dalek_b200_ctx *ctx, float *ms, int *launches);
+/* Same by name: "bucket_accumulate" (the figure above) or "decompress_R" (the R-decompression kernel of the last
+ * verify_batch call, the largest kernel of that path; summed over the pieces of a host-streamed call). */
+int dalek_b200_last_stage_ms(const dalek_b200_ctx *ctx, const char *stage, float *ms);
 /* Milliseconds between CUDA events recorded on the context's stream at entry of the last MSM / verify_batch /
  * precomputed-MSM call and after the last work it enqueued (all of the call's streams joined): the device time
  * of that call, copies of host-buffer calls included. */

@@ -18,11 +18,16 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
         "smsp__inst_executed_pipe_fmaheavy.sum", "sm__inst_executed_pipe_fmaheavy.sum"]
+# every per-pipe instruction / utilisation metric of the capture (FP64, IMAD / fmaheavy / fmalite, ALU, ...): the binding
+# roofline of these kernels is an issue pipe, so the whole breakdown is wanted (north_star: IMAD-pipe utilisation)
+PIPE_RE = ("sm__inst_executed_pipe_", "smsp__inst_executed_pipe_", "sm__pipe_", "smsp__pipe_", "smsp__issue_active", "sm__inst_issued",
+           "smsp__inst_issued")
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
 for row in rows[2:]:
     print("kernel:", row[hdr.index("Kernel Name")][:80])
     for h, u, v in zip(hdr, units, row):
-        if h in WANT:
+        pipe = h.startswith(PIPE_RE) and (h.endswith(".sum") or ".avg.pct_of_peak_sustained_active" in h) and v not in ("0", "")
+        if h in WANT or pipe:
             print("  %-84s %-10s %s" % (h, u, v))
