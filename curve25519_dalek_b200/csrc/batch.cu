@@ -258,6 +258,40 @@ k_prep_A(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ uniq, c
     for (int k = 0; k < 6; k++) o[k] = make_uint4(p.w[4 * k], p.w[4 * k + 1], p.w[4 * k + 2], p.w[4 * k + 3]);
 }
 
+// The reference's VerifyingKey already carries its decompressed point (E/verifying.rs:65-71) and verify_batch uses it
+// directly (batch.rs:236-238): when the caller passes those points (20 u64 radix-2^51 limbs X | Y | Z | T each) no key
+// is decompressed here.  Z = 1 (what VerifyingKey::from_bytes produces) costs nothing; another Z costs one inversion.
+template <int F64>
+__global__ void __launch_bounds__(128, PREP_MIN_BLOCKS)
+k_prep_A_points(const uint64_t *__restrict__ key_points, const uint32_t *__restrict__ uniq, const uint32_t *__restrict__ lo,
+                const uint32_t *__restrict__ hi, size_t i0, size_t cnt, ge_niels_packed *__restrict__ points_A)
+{
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i, slot;
+    if (uniq) { slot = *lo + j; if (slot >= *hi) return; i = uniq[slot]; } else { if (j >= cnt) return; i = slot = i0 + j; }
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(key_points + 20 * i);
+    uint64_t l[16];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { ulonglong2 v = src[k]; l[2 * k] = v.x; l[2 * k + 1] = v.y; }     // X, Y, Z (T is not needed)
+    fe x, y, z;
+    fe_from_limbs51(x, l); fe_from_limbs51(y, l + 5); fe_from_limbs51(z, l + 10);
+    uint32_t zw[8];
+    fe_tobytes_words(zw, z);
+    uint32_t rest = zw[0] ^ 1u;
+#pragma unroll
+    for (int k = 1; k < 8; k++) rest |= zw[k];
+    if (rest) {                                             // Z != 1: affine coordinates need 1 / Z
+        fe zi;
+        if (F64) fe_invert_f64(zi, z); else fe_invert(zi, z);
+        fe_mul(x, x, zi); fe_mul(y, y, zi);
+    }
+    ge_niels nl; ge_affine_to_niels(nl, x, y);
+    ge_niels_packed p; ge_niels_pack(p, nl);
+    uint4 *o = reinterpret_cast<uint4 *>(points_A + slot);
+#pragma unroll
+    for (int k = 0; k < 6; k++) o[k] = make_uint4(p.w[4 * k], p.w[4 * k + 1], p.w[4 * k + 2], p.w[4 * k + 3]);
+}
+
 // all keys distinct: scalar of key `pos` is the z h of its only signature
 __global__ void k_key_gather(const uint32_t *__restrict__ zh, const uint32_t *__restrict__ uniq, size_t nkeys, uint32_t *__restrict__ out)
 {
@@ -409,11 +443,13 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
         const uint32_t *lo = piece ? b.counters + piece : b.counters + 15, *hi = b.counters + 1 + piece;
         if (cnt) k_key_dedupe<<<cdiv(cnt, 256), 256, 0, st2>>>(d_keys, i0, cnt, b.table, b.tmask, b.rep, b.uniq, b.dense, b.counters);
         CUDA_TRY(ctx, cudaMemcpyAsync(b.counters + 1 + piece, b.counters, 4, cudaMemcpyDeviceToDevice, st2));
-        if (cnt && ctx->opt_decompress_f64) k_prep_A<1><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, b.uniq, lo, hi, i0, cnt, points_A, b.flags, b.bad_key);
+        if (cnt && ctx->key_points) k_prep_A_points<1><<<cdiv(cnt, 128), 128, 0, st2>>>(ctx->key_points, b.uniq, lo, hi, i0, cnt, points_A);
+        else if (cnt && ctx->opt_decompress_f64) k_prep_A<1><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, b.uniq, lo, hi, i0, cnt, points_A, b.flags, b.bad_key);
         else if (cnt) k_prep_A<0><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, b.uniq, lo, hi, i0, cnt, points_A, b.flags, b.bad_key);
         ctx->launches += cnt ? 2 : 0;
     } else if (cnt) {
-        if (ctx->opt_decompress_f64) k_prep_A<1><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, nullptr, nullptr, nullptr, i0, cnt, points_A, b.flags, b.bad_key);
+        if (ctx->key_points) k_prep_A_points<1><<<cdiv(cnt, 128), 128, 0, st2>>>(ctx->key_points, nullptr, nullptr, nullptr, i0, cnt, points_A);
+        else if (ctx->opt_decompress_f64) k_prep_A<1><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, nullptr, nullptr, nullptr, i0, cnt, points_A, b.flags, b.bad_key);
         else k_prep_A<0><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, nullptr, nullptr, nullptr, i0, cnt, points_A, b.flags, b.bad_key);
         ctx->launches++;
     }
@@ -611,7 +647,14 @@ struct ChunkOverride {
 };
 
 static int verify_host(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint64_t *msg_offsets, const uint8_t *sigs,
-                       const uint8_t *pubkeys, size_t n, size_t batch, int32_t *verdicts);
+                       const uint8_t *pubkeys, size_t n, size_t batch, int32_t *verdicts, const uint64_t *key_points = nullptr);
+
+// device pointer to the callers' decompressed key points for the duration of one call (..._points entry points)
+struct KeyPointsGuard {
+    dalek_b200_ctx *ctx;
+    KeyPointsGuard(dalek_b200_ctx *c, const uint64_t *p) : ctx(c) { c->key_points = p; }
+    ~KeyPointsGuard() { ctx->key_points = nullptr; }
+};
 
 extern "C" {
 
@@ -623,6 +666,23 @@ int ed25519_b200_verify_batch_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_f
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     return verify_dev(ctx, (const uint8_t *)d_msgs_flat, (const uint64_t *)d_msg_offsets, (const uint32_t *)d_sigs,
                       (const uint32_t *)d_pubkeys, n, 0, nullptr);
+}
+
+int ed25519_b200_verify_batch_flat_points_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat, const void *d_msg_offsets,
+                                              const void *d_sigs, const void *d_pubkeys, const void *d_key_points, size_t n)
+{
+    if (!ctx || (n && (!d_msg_offsets || !d_sigs || !d_pubkeys || !d_key_points))) return DALEK_E_INVALID_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    KeyPointsGuard guard(ctx, (const uint64_t *)d_key_points);
+    return verify_dev(ctx, (const uint8_t *)d_msgs_flat, (const uint64_t *)d_msg_offsets, (const uint32_t *)d_sigs,
+                      (const uint32_t *)d_pubkeys, n, 0, nullptr);
+}
+
+int ed25519_b200_verify_batch_flat_points(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint64_t *msg_offsets,
+                                          const uint8_t *sigs, const uint8_t *pubkeys, const uint64_t *key_points, size_t n)
+{
+    if (!ctx || (n && (!msg_offsets || !sigs || !pubkeys || !key_points))) return DALEK_E_INVALID_ARG;
+    return verify_host(ctx, msgs_flat, msg_offsets, sigs, pubkeys, n, 0, nullptr, key_points);
 }
 
 int ed25519_b200_verify_batches_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat, const void *d_msg_offsets,
@@ -653,7 +713,7 @@ int ed25519_b200_verify_batch_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat
 }  // extern "C"
 
 static int verify_host(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint64_t *msg_offsets, const uint8_t *sigs,
-                       const uint8_t *pubkeys, size_t n, size_t batch, int32_t *verdicts)
+                       const uint8_t *pubkeys, size_t n, size_t batch, int32_t *verdicts, const uint64_t *key_points)
 {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CallTimer timer(ctx);
@@ -667,6 +727,8 @@ static int verify_host(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint
     VerifyBufs b;
     if ((rc = verify_reserve(ctx, n, b))) return rc;
     uint8_t *d_msgs = (uint8_t *)ctx->misc1.p, *d_sigs = (uint8_t *)ctx->points_in.p, *d_keys = d_sigs + n * 64;
+    if (key_points && (rc = ws_reserve(ctx, ctx->key_pts, std::max<size_t>(1, n) * 160))) return rc;
+    KeyPointsGuard guard(ctx, key_points ? (const uint64_t *)ctx->key_pts.p : nullptr);
     uint64_t *d_offs = (uint64_t *)ctx->msg_offs.p;
     cudaStream_t st = ctx->stream, sc = ctx->stream_copy;
     CUDA_TRY(ctx, cudaMemsetAsync(b.flags, 0, 64, st));
@@ -687,6 +749,7 @@ static int verify_host(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint
             CUDA_TRY(ctx, cudaMemcpyAsync(d_offs + i0, msg_offsets + i0, (cnt + 1) * 8, cudaMemcpyHostToDevice, sc));
             CUDA_TRY(ctx, cudaMemcpyAsync(d_sigs + i0 * 64, sigs + i0 * 64, cnt * 64, cudaMemcpyHostToDevice, sc));
             CUDA_TRY(ctx, cudaMemcpyAsync(d_keys + i0 * 32, pubkeys + i0 * 32, cnt * 32, cudaMemcpyHostToDevice, sc));
+            if (key_points) CUDA_TRY(ctx, cudaMemcpyAsync((char *)ctx->key_pts.p + i0 * 160, key_points + 20 * i0, cnt * 160, cudaMemcpyHostToDevice, sc));
         }
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_grp[k], sc));
         if ((rc = verify_front(ctx, b, d_msgs, d_offs, (const uint32_t *)d_sigs, (const uint32_t *)d_keys, n, i0, i1, ctx->ev_grp[k], k))) return rc;

@@ -51,7 +51,8 @@ struct dalek_b200_ctx {
     bool async_open = false;       // a ..._partial_async call is in flight: its device span ends in ..._combine_dev
     // device workspaces (grown on demand, reused across calls)
     DevBuf scalars, points_in, points, digits, counts, offsets, sorted, buckets, red_a, red_b, red_c,
-        red_d, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums, msg_offs, sum_desc, sum_part, key_table, key_acc, task_order, sig_status, misc6;
+        red_d, key_pts, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums, msg_offs, sum_desc, sum_part, key_table, key_acc, task_order, sig_status, misc6;
+    const uint64_t *key_points = nullptr;   // device: callers' decompressed key points for the current verify_batch call (or null)
     int sum_desc_c = -1;
     bool base_table_ready = false;
     bool comb_attr_set = false;     // cudaFuncAttributeMaxDynamicSharedMemorySize set for the comb kernel on this device

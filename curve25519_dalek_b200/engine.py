@@ -65,6 +65,8 @@ def load_library():
     lib.ed25519_b200_verify_batch_flat.argtypes = [vp, vp, vp, vp, vp, sz]
     lib.ed25519_b200_verify_batch_flat_dev.argtypes = [vp, vp, vp, vp, vp, sz, sz]
     lib.ed25519_b200_verify_batches_flat.argtypes = [vp, vp, vp, vp, vp, sz, sz, vp]
+    lib.ed25519_b200_verify_batch_flat_points.argtypes = [vp, vp, vp, vp, vp, vp, sz]
+    lib.ed25519_b200_verify_batch_flat_points_dev.argtypes = [vp, vp, vp, vp, vp, vp, sz]
     lib.ed25519_b200_verify_batches_flat_dev.argtypes = [vp, vp, vp, vp, vp, sz, sz, vp]
     lib.dalek_b200_precomp_new.argtypes = [vp, vp, C.c_int, sz, C.POINTER(vp)]
     lib.dalek_b200_precomp_len.argtypes = [vp]
@@ -300,6 +302,12 @@ class Engine:
                                                                            _ptr(pubkeys), n, msgs_bytes))
         return self._check(self.lib.ed25519_b200_verify_batch_flat(self.h, _ptr(msgs_flat), _ptr(offsets), _ptr(sigs),
                                                                    _ptr(pubkeys), n))
+
+    def verify_batch_flat_points(self, msgs_flat, offsets, sigs, pubkeys, key_points, n, device_ptrs=False):
+        """verify_batch for callers holding VerifyingKeys: key_points = n x 20 u64 limbs, the decompressed point of each key
+        (E/verifying.rs:65-71); no key is decompressed inside the call."""
+        fn = self.lib.ed25519_b200_verify_batch_flat_points_dev if device_ptrs else self.lib.ed25519_b200_verify_batch_flat_points
+        return self._check(fn(self.h, _ptr(msgs_flat), _ptr(offsets), _ptr(sigs), _ptr(pubkeys), _ptr(key_points), n))
 
     def verify_batches_flat(self, msgs_flat, offsets, sigs, pubkeys, n, batch_size, device_ptrs=False):
         """Independent batches of `batch_size` signatures in one call: (rc, verdicts) with verdicts[k] the result of

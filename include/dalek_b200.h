@@ -58,14 +58,17 @@ typedef struct dalek_b200_ctx dalek_b200_ctx;
 int dalek_b200_init(int device, dalek_b200_ctx **out);
 void dalek_b200_destroy(dalek_b200_ctx *ctx);
 const char *dalek_b200_last_error(const dalek_b200_ctx *ctx);
-/* Tunables (none changes a result): "window_bits" (4..20, 0 = choose from n), "verify_chunk"
- * (signatures per transcript, default 64; see verify_batch below), "field_f64" (1 = bucket kernel
- * on the FP64-pipe field, default; 0 = IMAD.WIDE field), "host_chunks" (1..8, host-buffer MSM calls
- * stream their input in this many chunks, default 4), "verify_pieces" (1..8, same for verify_batch,
- * default 4), "decompress_f64" (1 = square-root exponentiation of decompression on the FP64 field, default), "dedupe_keys" (1 = decompress every distinct public key once and give it one MSM term,
- * default), "double_base_comb" (1 = fixed-base comb for double-base batches of >= 4096 pairs, default),
- * "precomp_tables" (1 = precomputations of >= 4096 points also keep the 2^(cw) P window tables; default 0:
- * measured, the 1.7 GB of randomly gathered table entries cost the bucket kernel what the shorter tail saves).
+/* Tunables.  None changes a result except "verify_chunk" (see verify_batch): "window_bits" (4..20, 0 = choose from n),
+ * "verify_chunk" (0, default: the reference's single transcript per batch; k > 0: opt-in, one transcript per k signatures --
+ * NOT reference-equivalent on inputs with small-order components), "field_f64" (1 = bucket kernel on the FP64-pipe field,
+ * default; 0 = IMAD.WIDE field), "acc_tma" (1 = the bucket kernel gathers points with TMA bulk copies, default 0: cp.async),
+ * "small_straus" (1 = fewer than 190 pairs run vartime Straus like the reference, default; 0 = bucket pipeline),
+ * "host_chunks" (1..8, host-buffer MSM calls stream their input in this many chunks, default 4), "verify_pieces" (1..8, same
+ * for verify_batch, default 4), "decompress_f64" (1 = square-root exponentiation of decompression on the FP64 field, default),
+ * "dedupe_keys" (1 = decompress every distinct public key once and give it one MSM term, default), "double_base_comb" (1 =
+ * fixed-base comb for double-base batches of >= 4096 pairs, default), "precomp_tables" (1 = precomputations of >= 4096 points
+ * also keep the 2^(cw) P window tables; default 0: measured, the 1.7 GB of randomly gathered table entries cost the bucket
+ * kernel what the shorter tail saves), "trace" (1 = per-stage device timeline of verify_batch on stderr).
  * Returns 0 or DALEK_E_INVALID_ARG. */
 int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
@@ -253,9 +256,14 @@ int dalek_b200_ristretto_vartime_msm(dalek_b200_ctx *ctx, const uint8_t *scalars
  * ED25519_ERR_POINT_DECOMPRESSION.  Then, in the reference's order
  * (E/batch.rs:208-250): non-canonical s -> ED25519_ERR_SCALAR_FORMAT; undecodable R or a
  * non-identity result -> ED25519_ERR_VERIFY; else 0.  No cofactor multiplication.
- * Coefficients z_i: for n <= verify_chunk the Merlin transcript is exactly the reference's; for
- * larger n the batch is cut into consecutive chunks of verify_chunk signatures, each with its own
- * transcript, and one combined equation is checked (DESIGN.md "transcript chunking").
+ * Coefficients z_i: exactly the reference's -- ONE Merlin transcript over the whole batch (batch.rs:168-222), whatever n
+ * is.  That transcript is a strictly sequential sponge (1.73 Keccak-f[1600] permutations per signature, one GPU thread:
+ * about 1 ms per 100 signatures), so callers with very large inputs either use ed25519_b200_verify_batches_flat (independent
+ * batches, each with the reference's transcript, hashed in parallel) or OPT INTO the option "verify_chunk" = k > 0: one
+ * transcript per k consecutive signatures and one combined equation.  The chunked mode is NOT reference-equivalent: its z_i
+ * differ from the reference's for n > k, and while the verdict is the same for every batch without small-order components
+ * (valid batches pass, invalid ones fail except with probability ~2^-128), for signatures or keys carrying small-order
+ * components the un-cofactored equation's verdict depends on the z_i modulo 8 and can differ from the reference's.
  */
 int ed25519_b200_verify_batch(dalek_b200_ctx *ctx, const uint8_t *const *msgs, const size_t *msg_lens,
                               const uint8_t *sigs, const uint8_t *pubkeys, size_t n);
@@ -268,10 +276,20 @@ int ed25519_b200_verify_batch_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat
 int ed25519_b200_verify_batch_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat,
                                        const void *d_msg_offsets, const void *d_sigs,
                                        const void *d_pubkeys, size_t n, size_t msgs_bytes);
+/* verify_batch for callers that hold VerifyingKeys: key_points[20 i ..] is the decompressed point of key i (X | Y | Z | T,
+ * radix-2^51 limbs, the reference's in-memory EdwardsPoint; what VerifyingKey::from_bytes computed once, E/verifying.rs:
+ * 65-71, :167-175) and pubkeys[32 i ..] its encoding (hashed as in batch.rs:179-191).  No key is decompressed inside the
+ * call -- the reference's verify_batch does not either (batch.rs:236-238) -- so a batch whose keys are all different costs
+ * what a batch with few keys costs.  The points are trusted to be the decodings of the encodings (as a VerifyingKey
+ * guarantees); Z = 1 is free, another Z costs one inversion per distinct key.  Never returns POINT_DECOMPRESSION. */
+int ed25519_b200_verify_batch_flat_points(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint64_t *msg_offsets,
+                                          const uint8_t *sigs, const uint8_t *pubkeys, const uint64_t *key_points, size_t n);
+int ed25519_b200_verify_batch_flat_points_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat, const void *d_msg_offsets,
+                                              const void *d_sigs, const void *d_pubkeys, const void *d_key_points, size_t n);
 /* Many independent batches in one call (2^14 batches of 256): signatures
  * [k * batch_size, min(n, (k+1) * batch_size)) form batch k and verdicts[k] receives what
  * ed25519_dalek::verify_batch (batch.rs:146-251) returns for that batch alone (0 / 1 / 3 / 4); each batch
- * uses exactly the reference's transcript.  The combined equation over all batches is tested first
+ * uses exactly the reference's transcript (whatever "verify_chunk" is).  The combined equation over all batches is tested first
  * (independent transcripts: a failing batch leaves it non-zero except with probability ~2^-128); only
  * when it fails are halves re-tested down to single batches, so a clean call costs the same as one large
  * verify_batch, and k failing batches add about k * log2(n / batch_size) partial re-tests.

@@ -371,3 +371,46 @@ def test_verify_batch_mixed_order_components_match_reference(eng, oracle, n):
         assert v == [oracle.verify_batch(msgs[k:k + 16], sigs[k:k + 16], pks[k:k + 16]) for k in range(0, n, 16)], trial
         outcomes.add(want)
     assert outcomes <= {OK, VERIFY}
+
+
+def test_verify_batch_with_key_points(eng, oracle):
+    """ed25519_b200_verify_batch_flat_points: the caller passes the decompressed point of every key (what the reference's
+    VerifyingKey holds, verifying.rs:65-71); verdicts and coefficients equal the byte-keyed call and the oracle, with Z = 1
+    points, with projectively scaled points (Z != 1), with repeated keys and with all keys distinct."""
+    import ctypes as C
+    import numpy as np
+    for n, distinct in ((60, False), (130, True)):
+        if distinct:
+            msgs, sigs, pks = make_batch(oracle, n, seed=31)
+        else:
+            rnd = random.Random(7)
+            seeds = [rnd.randbytes(32) for _ in range(5)]
+            msgs = [rnd.randbytes(40) for _ in range(n)]
+            pks = [oracle.public_key(seeds[i % 5]) for i in range(n)]
+            sigs = [oracle.sign(msgs[i], seeds[i % 5]) for i in range(n)]
+        flat, offs = _flat(msgs)
+        sg, pk = b"".join(sigs), b"".join(pks)
+        rc, limbs, ok = eng.decompress_batch(pk, n)
+        assert rc == 0 and all(ok)
+        pts = np.frombuffer(limbs, dtype=np.uint64).copy()
+        # every third point projectively rescaled (Z != 1): same point, different limbs
+        for i in range(0, n, 3):
+            p = oracle.p3_from_limbs([int(x) for x in pts[20 * i:20 * i + 20]])
+            q = oracle.sub(oracle.add(oracle.double(p), p), oracle.double(p))
+            pts[20 * i:20 * i + 20] = oracle.p3_limbs(q)
+        rc_o, zs_o = oracle.verify_batch(msgs, sigs, pks, want_zs=True)
+        assert rc_o == OK
+        assert eng.verify_batch_flat_points(flat, offs, sg, pk, pts, n) == OK
+        assert eng.last_zs(n) == zs_o
+        bad = bytearray(sg); bad[64 * 17 + 40] ^= 2
+        assert eng.verify_batch_flat_points(flat, offs, bytes(bad), pk, pts, n) == VERIFY
+        # the point is what enters the equation: a wrong point for one key fails the batch although its bytes are right
+        wrong = pts.copy(); wrong[20 * 4:20 * 5] = pts[20 * 5:20 * 6] if distinct else oracle.p3_limbs(oracle.basepoint())
+        assert eng.verify_batch_flat_points(flat, offs, sg, pk, wrong, n) == VERIFY
+        # device-resident form
+        import torch
+        dev = torch.device("cuda", 0)
+        d = [torch.from_numpy(x if x.dtype == np.uint8 else x.view(np.int64)).to(dev)
+             for x in (flat, offs, np.frombuffer(sg, dtype=np.uint8).copy(), np.frombuffer(pk, dtype=np.uint8).copy(), pts)]
+        assert eng.verify_batch_flat_points(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), d[4].data_ptr(), n,
+                                            device_ptrs=True) == OK
