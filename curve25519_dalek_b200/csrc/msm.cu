@@ -572,7 +572,7 @@ k_chunk_reduce_f64(const ge_p3_raw *__restrict__ S_in, uint32_t n_in, uint32_t m
     if (t >= n_out * nwin) return;
     const uint32_t w = t / n_out, q = t % n_out;
     const ge_p3_raw *S = S_in + (size_t)w * n_in + (size_t)q * m;
-    fe64 d2; { fe k; fe_const_2d(k); fe64_from_fe_limbs(d2, k); }
+    fe64 d2; fe64_const_2d(d2);
     ge64_p3 run, acc, x;
     load_p3_f64(run, S + (m - 1));
     acc = run;
@@ -695,18 +695,8 @@ __global__ void __launch_bounds__(32)
 k_combine(const ge_p3_raw *__restrict__ windows, int ranks, int nwin, int c, MsmResult *__restrict__ res)
 {
     const uint32_t role = threadIdx.x & 3;
-    fe64 d2; { fe k; fe_const_2d(k); fe64_from_fe_limbs(d2, k); }
-    w4f_point tot, x;
-    w4f_identity(tot);
-#pragma unroll 1
-    for (int w = nwin - 1; w >= 0; w--) {
-        if (w != nwin - 1) {
-#pragma unroll 1
-            for (int k = 0; k < c; k++) w4f_dbl(tot, role, k == c - 1);
-        }
-#pragma unroll 1
-        for (int r = 0; r < ranks; r++) { w4f_load(x, windows + (size_t)r * nwin + w); w4f_add(tot, x, d2, role); }
-    }
+    w4f_point tot;
+    w4f_horner(tot, windows, ranks, nwin, c, role);
     if (threadIdx.x != 0) return;
     ge_p3 total; w4f_to_p3(total, tot);
     uint32_t s[8];

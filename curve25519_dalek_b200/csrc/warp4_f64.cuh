@@ -7,12 +7,35 @@
 // squaring is 15 split products instead of 55 IMAD.WIDE plus pre-multiplications, an element is ten
 // 32-bit registers to select and shuffle instead of ten limbs with masks.  All 32 lanes of a warp must
 // execute these calls together (full-mask shuffles).
+//
+// The lane primitives are wrapped (w4_lane / w4_shfl / w4_shfl_down / w4_any) so that tests/host can run
+// the very same code on an emulated warp of host threads, with the operand-rule assertions of the host
+// field model switched on.
 #pragma once
 #include "ge64.cuh"
 
+#if defined(__CUDACC__)
+#define W4_DEV __device__ __forceinline__
+W4_DEV uint32_t w4_lane() { return threadIdx.x & 31u; }
+W4_DEV uint32_t w4_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+W4_DEV uint32_t w4_shfl_down(uint32_t v, int delta) { return __shfl_down_sync(0xffffffffu, v, delta); }
+W4_DEV bool w4_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+W4_DEV long long w4_bits(double d) { return __double_as_longlong(d); }
+W4_DEV double w4_from_bits(long long b) { return __longlong_as_double(b); }
+#else
+#include <string.h>
+#define W4_DEV static inline
+uint32_t w4_lane();                          // the host emulation of one warp (tests/host/w4_host_check.cpp)
+uint32_t w4_shfl(uint32_t v, int src);
+uint32_t w4_shfl_down(uint32_t v, int delta);
+bool w4_any(bool p);
+W4_DEV long long w4_bits(double d) { long long b; memcpy(&b, &d, 8); return b; }
+W4_DEV double w4_from_bits(long long b) { double d; memcpy(&d, &b, 8); return d; }
+#endif
+
 struct w4f_point { fe64 X, Y, Z, T; };       // extended point, coordinates of scale 1, replicated in the 4 lanes
 
-__device__ __forceinline__ void fe64_sel4(fe64 &o, const fe64 &a0, const fe64 &a1, const fe64 &a2, const fe64 &a3, uint32_t role)
+W4_DEV void fe64_sel4(fe64 &o, const fe64 &a0, const fe64 &a1, const fe64 &a2, const fe64 &a3, uint32_t role)
 {
 #pragma unroll
     for (int i = 0; i < 5; i++) {
@@ -22,44 +45,52 @@ __device__ __forceinline__ void fe64_sel4(fe64 &o, const fe64 &a0, const fe64 &a
 }
 
 // value held by lane `i` of this lane's group
-__device__ __forceinline__ void fe64_gbcast(fe64 &o, const fe64 &mine, int i)
+W4_DEV void fe64_gbcast(fe64 &o, const fe64 &mine, int i)
 {
-    const int src = (int)((threadIdx.x & 28u) | (uint32_t)i);
+    const int src = (int)((w4_lane() & 28u) | (uint32_t)i);
 #pragma unroll
     for (int k = 0; k < 5; k++) {
-        const long long v = __double_as_longlong(mine.v[k]);
-        const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
-        o.v[k] = __longlong_as_double((long long)(((uint64_t)hi << 32) | lo));
+        const long long v = w4_bits(mine.v[k]);
+        const uint32_t lo = w4_shfl((uint32_t)v, src), hi = w4_shfl((uint32_t)(v >> 32), src);
+        o.v[k] = w4_from_bits((long long)(((uint64_t)hi << 32) | lo));
     }
 }
 
 // scale-1 integer limbs (fe.cuh) -> balanced doubles of scale 1
-__device__ __forceinline__ void fe64_from_fe_limbs(fe64 &h, const fe &f)
+FE_HD void fe64_from_fe_limbs(fe64 &h, const fe &f)
 {
     fe64 t;
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         const uint64_t l = (uint64_t)f.v[2 * k] + ((uint64_t)f.v[2 * k + 1] << 26);       // < 2^51 + 2^26: exact in a double
+#if FE64_DEV
         t.v[k] = __longlong_as_double((long long)l | FE64_E52) - FE64_TWO52;
+#else
+        t.v[k] = (double)l;
+#endif
     }
     fe64_carry(h, t);
 }
 
-__device__ __forceinline__ void w4f_identity(w4f_point &p) { fe64_0(p.X); fe64_1(p.Y); fe64_1(p.Z); fe64_0(p.T); }
+W4_DEV void w4f_identity(w4f_point &p) { fe64_0(p.X); fe64_1(p.Y); fe64_1(p.Z); fe64_0(p.T); }
 
-__device__ __forceinline__ void w4f_load(w4f_point &p, const ge_p3_raw *src)
+W4_DEV void w4f_load(w4f_point &p, const ge_p3_raw *src)
 {
     ge_p3 q;
-    const uint4 *s = reinterpret_cast<const uint4 *>(src);
     ge_p3_raw r;
+#if defined(__CUDA_ARCH__)
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
 #pragma unroll
     for (int k = 0; k < 10; k++) { uint4 v = s[k]; r.w[4 * k] = v.x; r.w[4 * k + 1] = v.y; r.w[4 * k + 2] = v.z; r.w[4 * k + 3] = v.w; }
+#else
+    r = *src;
+#endif
     ge_p3_load_raw(q, r);
     fe64_from_fe_limbs(p.X, q.X); fe64_from_fe_limbs(p.Y, q.Y); fe64_from_fe_limbs(p.Z, q.Z); fe64_from_fe_limbs(p.T, q.T);
 }
 
 // p <- 2p (curve_models.rs:381-397 + :365-372).  T is refreshed only when want_t (the doubling before an addition).
-__device__ __forceinline__ void w4f_dbl(w4f_point &p, uint32_t role, bool want_t)
+W4_DEV void w4f_dbl(w4f_point &p, uint32_t role, bool want_t)
 {
     fe64 S, in, r, XX, YY, ZZ, S2, Yp, Ym, E, F, f, g;
     fe64_add(S, p.X, p.Y); fe64_carry(S, S);                  // squaring needs scale < 2
@@ -78,10 +109,25 @@ __device__ __forceinline__ void w4f_dbl(w4f_point &p, uint32_t role, bool want_t
     if (want_t) fe64_gbcast(p.T, r, 3);
 }
 
-// p <- p + q, both extended (edwards.rs:795-800 = :528-535 + curve_models.rs:411-430, :365-372); d2 = 2d as fe64
-__device__ __forceinline__ void w4f_add(w4f_point &p, const w4f_point &q, const fe64 &d2, uint32_t role)
+// shared second half of the additions: a, b, c (scale 1), D (scale 2); neg swaps the roles of D + c and D - c
+W4_DEV void w4f_add_tail(w4f_point &p, const fe64 &a, const fe64 &b, const fe64 &c, const fe64 &D, uint32_t neg, uint32_t role)
 {
-    fe64 qYpX, qYmX, qT2d, A, B, f, g, r, a, b, c, zz, D, E, H, DpC, DmC;
+    fe64 E, H, DpC, DmC, F, G, f, g, r;
+    fe64_sub(E, b, a); fe64_add(H, b, a);                     // 2, 2
+    fe64_add(DpC, D, c); fe64_sub(DmC, D, c);                 // 3, 3
+    fe64_carry(DmC, DmC);                                     // 1   (3 x 3 would break the operand rule of DmC * DpC)
+    F = DmC; fe64_cmov(F, DpC, neg);                          // T of the completed point
+    G = DpC; fe64_cmov(G, DmC, neg);                          // Z of the completed point
+    fe64_sel4(f, F, G, DmC, E, role);                         // X3 = F E, Y3 = G H, Z3 = DmC DpC, T3 = E H
+    fe64_sel4(g, E, H, DpC, H, role);
+    fe64_mul(r, f, g);                                        // <= 3 x 2
+    fe64_gbcast(p.X, r, 0); fe64_gbcast(p.Y, r, 1); fe64_gbcast(p.Z, r, 2); fe64_gbcast(p.T, r, 3);
+}
+
+// p <- p + q, both extended (edwards.rs:795-800 = :528-535 + curve_models.rs:411-430, :365-372); d2 = 2d as fe64
+W4_DEV void w4f_add(w4f_point &p, const w4f_point &q, const fe64 &d2, uint32_t role)
+{
+    fe64 qYpX, qYmX, qT2d, A, B, f, g, r, a, b, c, zz, D;
     fe64_add(qYpX, q.Y, q.X);                                 // 2
     fe64_sub(qYmX, q.Y, q.X);                                 // 2
     fe64_sub(A, p.Y, p.X); fe64_add(B, p.Y, p.X);             // 2, 2
@@ -91,16 +137,62 @@ __device__ __forceinline__ void w4f_add(w4f_point &p, const w4f_point &q, const 
     fe64_mul(r, f, g);                                        // <= 2 x 2
     fe64_gbcast(a, r, 0); fe64_gbcast(b, r, 1); fe64_gbcast(c, r, 2); fe64_gbcast(zz, r, 3);
     fe64_add(D, zz, zz);                                      // 2
-    fe64_sub(E, b, a); fe64_add(H, b, a);                     // 2, 2
-    fe64_add(DpC, D, c); fe64_sub(DmC, D, c);                 // 3, 3
-    fe64_carry(DmC, DmC);                                     // 1   (3 x 3 would break the operand rule of DmC * DpC)
-    fe64_sel4(f, DmC, DpC, DmC, E, role);                     // X3 = DmC E, Y3 = DpC H, Z3 = DmC DpC, T3 = E H
-    fe64_sel4(g, E, H, DpC, H, role);
-    fe64_mul(r, f, g);                                        // <= 3 x 2
-    fe64_gbcast(p.X, r, 0); fe64_gbcast(p.Y, r, 1); fe64_gbcast(p.Z, r, 2); fe64_gbcast(p.T, r, 3);
+    w4f_add_tail(p, a, b, c, D, 0u, role);
 }
 
-__device__ __forceinline__ void w4f_to_p3(ge_p3 &o, const w4f_point &p)
+// p <- p + q or p - q for a packed projective Niels point (curve_models.rs:411-452 + :365-372)
+W4_DEV void w4f_padd(w4f_point &p, const ge_pniels_packed &pk, uint32_t neg, uint32_t role)
+{
+    ge64_pniels q; ge64_pniels_unpack(q, pk);                 // coordinates in [0, 2^51): scale 2
+    fe64 qp = q.YpX, qm = q.YmX;
+    { fe64 t = qp; fe64_cmov(qp, qm, neg); fe64_cmov(qm, t, neg); }
+    fe64 A, B, f, g, r, a, b, c, zz, D;
+    fe64_sub(A, p.Y, p.X); fe64_add(B, p.Y, p.X);             // 2, 2
+    fe64_sel4(f, A, B, p.T, p.Z, role);
+    fe64_sel4(g, qm, qp, q.T2d, q.Z, role);
+    fe64_mul(r, f, g);                                        // <= 2 x 2
+    fe64_gbcast(a, r, 0); fe64_gbcast(b, r, 1); fe64_gbcast(c, r, 2); fe64_gbcast(zz, r, 3);
+    fe64_add(D, zz, zz);
+    w4f_add_tail(p, a, b, c, D, neg, role);
+}
+
+// copy of the point held by the group `delta_lanes` lanes above (delta_lanes a multiple of 4)
+W4_DEV void w4f_shfl_down(w4f_point &o, const w4f_point &p, int delta_lanes)
+{
+    const fe64 *src[4] = {&p.X, &p.Y, &p.Z, &p.T};
+    fe64 *dst[4] = {&o.X, &o.Y, &o.Z, &o.T};
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const long long v = w4_bits(src[c]->v[k]);
+            const uint32_t lo = w4_shfl_down((uint32_t)v, delta_lanes), hi = w4_shfl_down((uint32_t)(v >> 32), delta_lanes);
+            dst[c]->v[k] = w4_from_bits((long long)(((uint64_t)hi << 32) | lo));
+        }
+}
+
+W4_DEV void w4f_to_p3(ge_p3 &o, const w4f_point &p)
 {
     fe64_to_fe(o.X, p.X); fe64_to_fe(o.Y, p.Y); fe64_to_fe(o.Z, p.Z); fe64_to_fe(o.T, p.T);
+}
+
+// 2d (u64/constants.rs:54) as balanced doubles
+FE_HD void fe64_const_2d(fe64 &d2) { fe k; fe_const_2d(k); fe64_from_fe_limbs(d2, k); }
+
+// Horner over windows (pippenger.rs:159): total = total * 2^c + sum over ranks of window w, from the top window down.
+// windows: rank-major (ranks x nwin raw points).  The result is replicated in the four lanes of every group.
+W4_DEV void w4f_horner(w4f_point &tot, const ge_p3_raw *windows, int ranks, int nwin, int c, uint32_t role)
+{
+    fe64 d2; fe64_const_2d(d2);
+    w4f_point x;
+    w4f_identity(tot);
+#pragma unroll 1
+    for (int w = nwin - 1; w >= 0; w--) {
+        if (w != nwin - 1) {
+#pragma unroll 1
+            for (int k = 0; k < c; k++) w4f_dbl(tot, role, k == c - 1);
+        }
+#pragma unroll 1
+        for (int r = 0; r < ranks; r++) { w4f_load(x, windows + (size_t)r * nwin + w); w4f_add(tot, x, d2, role); }
+    }
 }

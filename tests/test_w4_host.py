@@ -1,0 +1,83 @@
+"""The product's 4-lane FP64 point code (csrc/warp4_f64.cuh: the Horner pass of k_combine; csrc/straus_vt.cuh: NAF,
+table of odd multiples and main loop of the vartime Straus path) executed on the CPU by an emulated warp of 32 host
+threads (tests/host/w4_host_check.cpp) with the operand-rule assertions of the host field model switched on, against
+the oracle.  CPU only: the emulation is test infrastructure, not a fallback of the product."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import pytest
+
+import pyref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def w4():
+    src = os.path.join(ROOT, "tests", "host", "w4_host_check.cpp")
+    so = os.path.join(ROOT, "tests", "host", "libw4host.so")
+    csrc = os.path.join(ROOT, "curve25519_dalek_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("fe.cuh", "fe64.cuh", "ge.cuh", "ge64.cuh", "warp4_f64.cuh", "straus_vt.cuh", "constants.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", so, src, "-lpthread"])
+    return C.CDLL(so)
+
+
+def _points(oracle, rnd, n, special=True):
+    B = oracle.basepoint()
+    pts = [oracle.scalarmul(rnd.randrange(pyref.L).to_bytes(32, "little"), B) for _ in range(n)]
+    if special and n >= 4:
+        pts[1] = oracle.identity()
+        pts[2] = oracle.decompress((pyref.p - 1).to_bytes(32, "little"))       # (0, -1), order 2
+        pts[3] = oracle.decompress((0).to_bytes(32, "little"))                 # order 4
+    return pts
+
+
+@pytest.mark.parametrize("ranks,nwin,c", [(1, 17, 16), (3, 4, 20), (8, 5, 4), (2, 1, 7)])
+def test_horner_pass_matches_oracle(w4, oracle, ranks, nwin, c):
+    """w4f_horner (k_combine): sum_w 2^(c w) * sum_r W[r][w], doublings and additions on four lanes."""
+    rnd = random.Random(ranks * 1000 + nwin)
+    pts = _points(oracle, rnd, ranks * nwin)
+    want = oracle.identity()
+    for w in range(nwin - 1, -1, -1):
+        want = oracle.mul_by_pow_2(want, c) if w != nwin - 1 else want
+        for r in range(ranks):
+            want = oracle.add(want, pts[r * nwin + w])
+    out = (C.c_uint8 * 32)()
+    buf = b"".join(oracle.compress(p) for p in pts)
+    assert w4.h_w4f_horner(out, buf, ranks, nwin, c) == 1
+    assert bytes(out) == oracle.compress(want)
+
+
+def test_device_naf_is_the_reference_naf(w4, oracle):
+    rnd = random.Random(5)
+    for t in range(300):
+        v = [0, 1, 2**255 - 1, 2**256 - 1, pyref.L - 1][t] if t < 5 else (rnd.randrange(2**255) if t % 3 else rnd.randrange(2**256))
+        sb = v.to_bytes(32, "little")
+        out = (C.c_int8 * 264)()
+        w4.h_naf5(out, sb)
+        d = list(out)
+        assert sum(x << i for i, x in enumerate(d)) == v
+        assert all(x == 0 or (x % 2 and -16 < x < 16) for x in d)
+        if v < 2**255:                                            # reference-legal scalars: exactly scalar.rs:955-1007
+            assert d[:256] == oracle.naf(sb, 5) and not any(d[256:])
+
+
+@pytest.mark.parametrize("n", [1, 8, 9])
+def test_straus_vartime_matches_oracle(w4, oracle, n):
+    """straus_vt.cuh end to end on the emulated warp(s): NafLookupTable5 tables, main loop with per-group accumulators,
+    sum of the groups -- against the oracle's vartime Straus (straus.rs:159-200)."""
+    rnd = random.Random(40 + n)
+    pts = _points(oracle, rnd, n, special=n >= 7)
+    scalars = [rnd.randrange(pyref.L).to_bytes(32, "little") for _ in range(n)]
+    if n >= 7:
+        scalars[0] = (0).to_bytes(32, "little")
+        scalars[4] = (1).to_bytes(32, "little")
+        scalars[5] = (pyref.L - 1).to_bytes(32, "little")
+        scalars[6] = (2**255 - 1).to_bytes(32, "little")
+    want = oracle.compress(oracle.msm("straus_vartime", scalars, pts))
+    out = (C.c_uint8 * 32)()
+    assert w4.h_straus_vartime(out, b"".join(scalars), b"".join(oracle.compress(p) for p in pts), n) == 1
+    assert bytes(out) == want
