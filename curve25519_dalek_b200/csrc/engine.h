@@ -42,6 +42,7 @@ struct dalek_b200_ctx {
     long opt_verify_pieces = 4; // host-buffer verify_batch calls stream the signatures in this many pieces
     long opt_decompress_f64 = 1; // square-root exponentiation of point decompression on the FP64-pipe field
     long opt_acc_tma = 0;       // bucket kernel gathers points with TMA bulk copies + mbarriers instead of cp.async (A/B option)
+    long opt_transcript_warp = 1; // up to 2048 Merlin transcripts per launch run one WARP each (25-lane Keccak); 0 = one thread each
     long opt_small_straus = 1;  // fewer than 190 pairs: vartime Straus (3 launches) instead of the bucket pipeline
     long opt_field_f64 = 1;     // bucket kernel on the FP64 pipe (fe64.cuh) instead of IMAD.WIDE (fe.cuh)
     // timing of the dominant kernel in the last call

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../curve25519_dalek_b200/csrc/straus_vt.cuh"
+#include "../../curve25519_dalek_b200/csrc/transcript_warp.cuh"
 
 // ---- the emulated warp -------------------------------------------------------------------------------------------
 static pthread_barrier_t g_bar;
@@ -122,5 +123,20 @@ int h_straus_vartime(uint8_t *out, const uint8_t *scalars, const uint8_t *points
 
 // NAF digits of one scalar (NAF_LEN of them)
 void h_naf5(int8_t *out, const uint8_t *scalar) { uint32_t s[8]; memcpy(s, scalar, 32); naf5(out, s); }
+
+// one Merlin transcript of verify_batch on the emulated warp: hrams n x 64 B, sigs n x 64 B (R || s) -> zs n x 16 B
+void h_merlin_zs(uint8_t *zs, const uint8_t *hrams, const uint8_t *sigs, uint64_t n)
+{
+    std::vector<uint32_t> h(16 * n), sg(16 * n), z(4 * n);
+    memcpy(h.data(), hrams, 64 * n); memcpy(sg.data(), sigs, 64 * n);
+    run_warp([&](uint32_t) { merlin_zs_warp(h.data(), sg.data(), n, z.data()); });
+    memcpy(zs, z.data(), 16 * n);
+}
+// the constant prefix state and positions compiled into the product
+void h_merlin_prefix(uint64_t *lanes25, uint32_t *pos, uint32_t *pos_begin)
+{
+    for (uint32_t l = 0; l < 25; l++) lanes25[l] = merlin_prefix_lane(l);
+    *pos = MERLIN_PREFIX_POS; *pos_begin = MERLIN_PREFIX_POS_BEGIN;
+}
 
 }  // extern "C"

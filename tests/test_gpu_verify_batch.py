@@ -60,6 +60,26 @@ def test_verify_batch_chunk_option(eng, oracle):
             eng.set_option("verify_chunk", 0)
 
 
+def test_transcript_kernels_agree(eng, oracle):
+    """The Merlin transcript runs on one WARP (25-lane Keccak, csrc/transcript_warp.cuh) when a launch has few transcripts
+    and on one thread per transcript otherwise; option `transcript_warp` selects.  Both must draw the oracle's z_i: one
+    transcript over 301 signatures (n = 53 and 219 end exactly on a rate-block boundary), and chunks of 7."""
+    for n in (53, 219, 301):
+        msgs, sigs, pks = make_batch(oracle, n, seed=5000 + n, msg_len=33)
+        for chunk in (0, 7):
+            rc_o, zs_o = oracle.verify_batch(msgs, sigs, pks, chunk=chunk, want_zs=True)
+            assert rc_o == OK
+            for warp in (1, 0):
+                eng.set_option("transcript_warp", warp)
+                eng.set_option("verify_chunk", chunk)
+                try:
+                    assert run(eng, msgs, sigs, pks) == OK
+                    assert eng.last_zs(n) == zs_o, (n, chunk, warp)
+                finally:
+                    eng.set_option("transcript_warp", 1)
+                    eng.set_option("verify_chunk", 0)
+
+
 def test_verify_batch_negative_controls(eng, oracle):
     msgs, sigs, pks = make_batch(oracle, 33, seed=99, msg_len=59)
     cases = []

@@ -19,7 +19,7 @@ def w4():
     src = os.path.join(ROOT, "tests", "host", "w4_host_check.cpp")
     so = os.path.join(ROOT, "tests", "host", "libw4host.so")
     csrc = os.path.join(ROOT, "curve25519_dalek_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("fe.cuh", "fe64.cuh", "ge.cuh", "ge64.cuh", "warp4_f64.cuh", "straus_vt.cuh", "constants.cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("fe.cuh", "fe64.cuh", "ge.cuh", "ge64.cuh", "warp4_f64.cuh", "straus_vt.cuh", "transcript_warp.cuh", "constants.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", so, src, "-lpthread"])
     return C.CDLL(so)
@@ -80,4 +80,38 @@ def test_straus_vartime_matches_oracle(w4, oracle, n):
     want = oracle.compress(oracle.msm("straus_vartime", scalars, pts))
     out = (C.c_uint8 * 32)()
     assert w4.h_straus_vartime(out, b"".join(scalars), b"".join(oracle.compress(p) for p in pts), n) == 1
+    assert bytes(out) == want
+
+
+def test_merlin_prefix_constant(w4, oracle):
+    """The state after Transcript::new(b"ed25519 batch verification") (transcript.rs:54-61) that transcript_warp.cuh
+    holds as a constant, recomputed with the oracle's STROBE / Merlin code."""
+    class Strobe(C.Structure):
+        _fields_ = [("st", C.c_uint8 * 200), ("pos", C.c_uint8), ("pos_begin", C.c_uint8), ("cur_flags", C.c_uint8)]
+    t = Strobe()
+    lab = b"ed25519 batch verification"
+    oracle.lib.merlin_new(C.byref(t), lab, C.c_size_t(len(lab)))
+    lanes = (C.c_uint64 * 25)(); pos = C.c_uint32(); pb = C.c_uint32()
+    w4.h_merlin_prefix(lanes, C.byref(pos), C.byref(pb))
+    st = bytes(t.st)
+    assert list(lanes) == [int.from_bytes(st[8 * i:8 * i + 8], "little") for i in range(25)]
+    assert (pos.value, pb.value) == (t.pos, t.pos_begin)
+
+
+@pytest.mark.parametrize("n", [1, 2, 9, 53])
+def test_warp_transcript_draws_the_reference_coefficients(w4, oracle, n):
+    """merlin_zs_warp (the 25-lane Keccak and the closed-form byte stream of the transcript) on the emulated warp: every
+    z_i equals what the oracle's Merlin transcript draws (batch.rs:168-222).  n = 53 ends exactly on a rate-block
+    boundary (no forced permutation before the KEY operation)."""
+    rnd = random.Random(n)
+    msgs = [rnd.randbytes(rnd.randrange(0, 40)) for _ in range(n)]
+    sks = [rnd.randbytes(32) for _ in range(n)]
+    pks = [oracle.public_key(s) for s in sks]
+    sigs = [oracle.sign(m, s) for m, s in zip(msgs, sks)]
+    rc, want = oracle.verify_batch(msgs, sigs, pks, want_zs=True)
+    assert rc == 0
+    import hashlib
+    hr = b"".join(hashlib.sha512(sigs[i][:32] + pks[i] + msgs[i]).digest() for i in range(n))
+    out = (C.c_uint8 * (16 * n))()
+    w4.h_merlin_zs(out, hr, b"".join(sigs), C.c_uint64(n))
     assert bytes(out) == want
