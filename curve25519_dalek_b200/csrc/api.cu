@@ -3,6 +3,7 @@
 // constant-time / Ristretto entry points in straus.cu.
 #include <cstring>
 #include <new>
+#include <random>
 
 #include "../../include/dalek_b200.h"
 #include "engine.h"
@@ -23,6 +24,7 @@ int dalek_b200_init(int device, dalek_b200_ctx **out)
     if (!ctx) return DALEK_E_NOMEM;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    try { std::random_device rd; for (int i = 0; i < 4; i++) ctx->hash_seed[i] ^= rd(); } catch (...) { }   // results never depend on it
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);       // (greatest priority is the lower number)
     if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
@@ -182,7 +184,7 @@ static int finish_msm(dalek_b200_ctx *ctx, const ge_p3_raw *d_windows, int ranks
     CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->result.p, sizeof(MsmResult), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
+    if ((ms = elapsed_ms(ctx->ev_a, ctx->ev_b)) >= 0.f) ctx->last_kernel_ms = ms;
     if (out_compressed) memcpy(out_compressed, h->compressed, 32);
     if (out_limbs) memcpy(out_limbs, h->limbs, 160);
     if (is_identity) *is_identity = h->is_identity;
@@ -292,7 +294,7 @@ static int partial_enqueue(dalek_b200_ctx *ctx, const void *scalars, const void 
 static void read_kernel_ms(dalek_b200_ctx *ctx)
 {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
+    if ((ms = elapsed_ms(ctx->ev_a, ctx->ev_b)) >= 0.f) ctx->last_kernel_ms = ms;
 }
 
 static int partial_common(dalek_b200_ctx *ctx, const void *scalars, const void *points, bool on_device, int point_fmt,
@@ -364,7 +366,7 @@ int msm_combine_records(dalek_b200_ctx *ctx, const void *records, bool on_device
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (ctx->async_open) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ctx->ev_call0, ctx->ev_call1) == cudaSuccess) ctx->last_call_ms = ms;
+        if ((ms = elapsed_ms(ctx->ev_call0, ctx->ev_call1)) >= 0.f) ctx->last_call_ms = ms;
         read_kernel_ms(ctx);                                     // the bucket kernels of the partial call
         ctx->async_open = false;
     }

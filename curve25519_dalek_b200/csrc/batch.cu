@@ -232,7 +232,7 @@ k_prep_R(const uint32_t *__restrict__ sigs, size_t cnt, ge_niels_packed *__restr
 __global__ void __launch_bounds__(256)
 k_key_dedupe(const uint32_t *__restrict__ keys /* all n keys */, size_t i0, size_t cnt, uint32_t *__restrict__ table,
              uint32_t tmask, uint32_t *__restrict__ rep, uint32_t *__restrict__ uniq, uint32_t *__restrict__ dense,
-             uint32_t *__restrict__ uniq_count)
+             uint32_t *__restrict__ uniq_count, uint4 hash_seed)
 {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= cnt) return;
@@ -240,9 +240,13 @@ k_key_dedupe(const uint32_t *__restrict__ keys /* all n keys */, size_t i0, size
     uint32_t k[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) k[q] = keys[8 * (size_t)i + q];
-    uint32_t h = k[0] * 0x9E3779B1u ^ k[1] * 0x85EBCA77u ^ k[2] * 0xC2B2AE3Du ^ k[3] * 0x27D4EB2Fu ^
-                 k[4] * 0x165667B1u ^ k[5] * 0xD3A2646Cu ^ k[6] * 0xFD7046C5u ^ k[7] * 0xB55A4F09u;
-    h ^= h >> 15;
+    // keyed per context (hash_seed is drawn at dalek_b200_init): the slot sequence of attacker-chosen key bytes cannot be
+    // predicted, so crafted keys cannot be made to pile up in one probe run
+    uint32_t h = hash_seed.x;
+#pragma unroll
+    for (int q = 0; q < 8; q++) { h = (h ^ k[q]) * 0x9E3779B1u; h ^= h >> 15; h += (q & 1) ? hash_seed.y : hash_seed.z; }
+    h = (h ^ hash_seed.w) * 0x85EBCA77u;
+    h ^= h >> 13;
     uint32_t slot = h & tmask;
     for (;;) {
         uint32_t cur = atomicCAS(&table[slot], 0xffffffffu, i);
@@ -464,7 +468,8 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
     if (ctx->opt_dedupe_keys) {
         // keys first seen in this piece are uniq[counters[piece] .. counters[1 + piece])  (counters[15] = 0 for piece 0)
         const uint32_t *lo = piece ? b.counters + piece : b.counters + 15, *hi = b.counters + 1 + piece;
-        if (cnt) k_key_dedupe<<<cdiv(cnt, 256), 256, 0, st2>>>(d_keys, i0, cnt, b.table, b.tmask, b.rep, b.uniq, b.dense, b.counters);
+        if (cnt) k_key_dedupe<<<cdiv(cnt, 256), 256, 0, st2>>>(d_keys, i0, cnt, b.table, b.tmask, b.rep, b.uniq, b.dense, b.counters,
+                                                               make_uint4(ctx->hash_seed[0], ctx->hash_seed[1], ctx->hash_seed[2], ctx->hash_seed[3]));
         CUDA_TRY(ctx, cudaMemcpyAsync(b.counters + 1 + piece, b.counters, 4, cudaMemcpyDeviceToDevice, st2));
         if (cnt && ctx->key_points) k_prep_A_points<1><<<cdiv(cnt, 128), 128, 0, st2>>>(ctx->key_points, b.uniq, lo, hi, i0, cnt, points_A);
         else if (cnt && ctx->opt_decompress_f64) k_prep_A<1><<<cdiv(cnt, 128), 128, 0, st2>>>(d_keys, b.uniq, lo, hi, i0, cnt, points_A, b.flags, b.bad_key);
@@ -593,10 +598,10 @@ static int verify_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, int p
     CUDA_TRY(ctx, cudaMemcpyAsync(hflags, b.flags, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
+    if ((ms = elapsed_ms(ctx->ev_a, ctx->ev_b)) >= 0.f) ctx->last_kernel_ms = ms;
     ctx->last_prep_ms = 0.f;
     for (int k = 0; k < ctx->prep_pieces; k++)
-        if (cudaEventElapsedTime(&ms, ctx->ev_prep[k][0], ctx->ev_prep[k][1]) == cudaSuccess) ctx->last_prep_ms += ms;
+        if ((ms = elapsed_ms(ctx->ev_prep[k][0], ctx->ev_prep[k][1])) >= 0.f) ctx->last_prep_ms += ms;
     trace_dump(ctx);
     // error precedence follows the reference: VerifyingKey::from_bytes happens before verify_batch
     // can be called (PointDecompression); then s canonicity (batch.rs:208-211); then R / equation.
@@ -625,17 +630,30 @@ static int verify_batches_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t 
     CUDA_TRY(ctx, cudaMemcpyAsync(status.data(), ctx->misc6.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     std::vector<uint8_t> eq_ok(nb, 0);
-    std::vector<std::pair<size_t, size_t>> todo{{0, nb}};               // ranges of batches still to be tested
+    // ranges of batches still to be classified; `known_bad`: the range is known to contain a failing batch (its parent
+    // failed and its sibling verified), so its own equation need not be evaluated again
+    struct Range { size_t k0, k1; bool known_bad; };
+    std::vector<Range> todo{{0, nb, false}};
     while (!todo.empty()) {
-        auto [k0, k1] = todo.back();
+        const Range r = todo.back();
         todo.pop_back();
         bool ident = false;
-        if ((rc = verify_equation(ctx, b, n, nkeys, k0 * batch, std::min(n, k1 * batch), &ident))) return rc;
-        if (ident) { for (size_t k = k0; k < k1; k++) eq_ok[k] = 1; continue; }
-        if (k1 - k0 == 1) continue;
-        const size_t mid = k0 + (k1 - k0) / 2;
-        todo.push_back({mid, k1});
-        todo.push_back({k0, mid});
+        if (!r.known_bad) {
+            if ((rc = verify_equation(ctx, b, n, nkeys, r.k0 * batch, std::min(n, r.k1 * batch), &ident))) return rc;
+            if (ident) { for (size_t k = r.k0; k < r.k1; k++) eq_ok[k] = 1; continue; }
+        }
+        if (r.k1 - r.k0 == 1) continue;                                  // a single failing batch
+        const size_t mid = r.k0 + (r.k1 - r.k0) / 2;
+        // left half first; if it verifies, the right half is the failing one
+        bool left_ok = false;
+        if ((rc = verify_equation(ctx, b, n, nkeys, r.k0 * batch, std::min(n, mid * batch), &left_ok))) return rc;
+        if (left_ok) {
+            for (size_t k = r.k0; k < mid; k++) eq_ok[k] = 1;
+            todo.push_back({mid, r.k1, true});
+        } else {
+            todo.push_back({mid, r.k1, false});
+            todo.push_back({r.k0, mid, true});
+        }
     }
     int any = 0;
     for (size_t k = 0; k < nb; k++) {

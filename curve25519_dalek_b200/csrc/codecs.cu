@@ -205,7 +205,7 @@ static int run_pieces(dalek_b200_ctx *ctx, const uint8_t *in, size_t in_sz, uint
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
+    if ((ms = elapsed_ms(ctx->ev_a, ctx->ev_b)) >= 0.f) ctx->last_kernel_ms = ms;
     ctx->last_kernel_launches = (int)k;
     return 0;
 }

@@ -54,6 +54,7 @@ struct dalek_b200_ctx {
     DevBuf scalars, points_in, points, digits, counts, offsets, sorted, buckets, red_a, red_b, red_c,
         red_d, key_pts, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums, msg_offs, sum_desc, sum_part, key_table, key_acc, task_order, sig_status, misc6;
     const uint64_t *key_points = nullptr;   // device: callers' decompressed key points for the current verify_batch call (or null)
+    uint32_t hash_seed[4] = {0x243F6A88u, 0x85A308D3u, 0x13198A2Eu, 0x03707344u};   // key of the public-key de-duplication hash, redrawn per context
     int sum_desc_c = -1;
     bool base_table_ready = false;
     bool comb_attr_set = false;     // cudaFuncAttributeMaxDynamicSharedMemorySize set for the comb kernel on this device
@@ -73,6 +74,16 @@ struct dalek_b200_ctx {
         }                                                                                        \
     } while (0)
 
+// Milliseconds between two events, or a negative value if either was never recorded / has not completed; a failure does
+// not stay behind as the context's "last CUDA error" (a later cudaGetLastError() would report it for an innocent call).
+inline float elapsed_ms(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) return ms;
+    cudaGetLastError();
+    return -1.f;
+}
+
 // Device time of one blocking call: an event on the main stream at entry, one after everything the call enqueued
 // (the other streams are joined into the main one before a call returns); read with dalek_b200_last_call_ms.
 struct CallTimer {
@@ -83,7 +94,7 @@ struct CallTimer {
         if (!ctx) return;
         float ms = 0.f;
         if (cudaEventRecord(ctx->ev_call1, ctx->stream) == cudaSuccess && cudaEventSynchronize(ctx->ev_call1) == cudaSuccess &&
-            cudaEventElapsedTime(&ms, ctx->ev_call0, ctx->ev_call1) == cudaSuccess)
+            (ms = elapsed_ms(ctx->ev_call0, ctx->ev_call1)) >= 0.f)
             ctx->last_call_ms = ms;
     }
 };

@@ -564,7 +564,7 @@ __device__ __forceinline__ void load_p3_f64(ge64_p3 &o, const ge_p3_raw *src)
 // Level 1 of the bucket reduction (see k_chunk_reduce below) with ONE THREAD per chunk of m buckets on the
 // FP64-pipe field: 2^(c-1) W / m chunks (32768 for 2^20 pairs) are enough threads for the throughput field, and
 // a thread's 2(m-1) additions need no shuffles.  S_q = sum_r B_{qm+r},  W_q = sum_r (r+1) B_{qm+r}.
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(32)
 k_chunk_reduce_f64(const ge_p3_raw *__restrict__ S_in, uint32_t n_in, uint32_t m, uint32_t n_out, uint32_t nwin,
                    ge_p3_raw *__restrict__ S_out, ge_p3_raw *__restrict__ W_out)
 {
@@ -576,9 +576,12 @@ k_chunk_reduce_f64(const ge_p3_raw *__restrict__ S_in, uint32_t n_in, uint32_t m
     ge64_p3 run, acc, x;
     load_p3_f64(run, S + (m - 1));
     acc = run;
+    ge_p3 nxt;                                              // the next bucket is loaded one iteration ahead
+    if (m > 1) load_p3(nxt, S + (m - 2));
 #pragma unroll 1
     for (uint32_t r = m - 1; r-- > 0;) {
-        load_p3_f64(x, S + r);
+        fe64_from_fe_limbs(x.X, nxt.X); fe64_from_fe_limbs(x.Y, nxt.Y); fe64_from_fe_limbs(x.Z, nxt.Z); fe64_from_fe_limbs(x.T, nxt.T);
+        if (r > 0) load_p3(nxt, S + (r - 1));
         ge64_add_p3(run, run, x, d2);
         ge64_add_p3(acc, acc, run, d2);
     }
@@ -837,7 +840,7 @@ int msm_reduce_finish(dalek_b200_ctx *ctx, int c, ge_p3_raw *d_windows, MsmResul
         uint32_t m = lvl_m[l], n_out = lvl_nout[l];
         ge_p3_raw *S_out = pool + pos, *W_out = pool + pos + (size_t)n_out * nwin;
         if (l == 0 && ctx->opt_field_f64 && n_in % m == 0)
-            k_chunk_reduce_f64<<<cdiv((size_t)n_out * nwin, 64), 64, 0, st>>>(S_in, n_in, m, n_out, nwin, S_out, W_out);
+            k_chunk_reduce_f64<<<cdiv((size_t)n_out * nwin, 32), 32, 0, st>>>(S_in, n_in, m, n_out, nwin, S_out, W_out);   // small CTAs: 1024 warps spread evenly over the SMs
         else
             k_chunk_reduce<<<cdiv((size_t)n_out * nwin * 4, 128), 128, 0, st>>>(S_in, n_in, m, l == 0 ? 1u : 0u, n_out, nwin, S_out, W_out);
         ctx->launches++;

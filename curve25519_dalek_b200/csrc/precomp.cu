@@ -254,7 +254,7 @@ int dalek_b200_precomp_mixed_msm(dalek_b200_ctx *ctx, const dalek_b200_precomp *
     if (pre->ristretto) CUDA_TRY(ctx, cudaMemcpyAsync(h_enc, d_enc, 32, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
+    if ((ms = elapsed_ms(ctx->ev_a, ctx->ev_b)) >= 0.f) ctx->last_kernel_ms = ms;
     if (*h_bad) return DALEK_NONE;                      // optional_mixed_multiscalar_mul: a dynamic point was None
     if (out_compressed) memcpy(out_compressed, pre->ristretto ? h_enc : (const uint8_t *)h->compressed, 32);
     if (out_limbs) memcpy(out_limbs, h->limbs, 160);

@@ -363,7 +363,7 @@ static int double_base_status(dalek_b200_ctx *ctx, const DoubleBasePlan &plan, i
     CUDA_TRY(ctx, cudaMemcpyAsync(hs, plan.d_status, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
+    if ((ms = elapsed_ms(ctx->ev_a, ctx->ev_b)) >= 0.f) ctx->last_kernel_ms = ms;
     ctx->last_kernel_launches = 1;
     *h_status = *hs;
     return 0;
@@ -470,7 +470,7 @@ int dalek_b200_edwards_ct_msm(dalek_b200_ctx *ctx, const uint8_t *scalars, const
     CUDA_TRY(ctx, cudaMemcpyAsync(h_bad, ctx->flags.p, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     float ms = 0.f;
-    if (n && cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) == cudaSuccess) ctx->last_kernel_ms = ms;
+    if (n && (ms = elapsed_ms(ctx->ev_a, ctx->ev_b)) >= 0.f) ctx->last_kernel_ms = ms;
     if (*h_bad) { ctx->last_error = "a compressed point does not decode (multiscalar_mul takes points, not Options)"; return DALEK_E_INVALID_ARG; }
     if (out_compressed) memcpy(out_compressed, h->compressed, 32);
     if (out_limbs) memcpy(out_limbs, h->limbs, 160);
