@@ -22,6 +22,8 @@
 #include "hash.cuh"
 #include "sc.cuh"
 #include "transcript_warp.cuh"
+#include "ge64.cuh"
+#include "warp4_f64.cuh"
 
 static inline unsigned cdiv(size_t a, unsigned b) { return (unsigned)((a + b - 1) / b); }
 
@@ -392,6 +394,96 @@ __global__ void k_batch_status(const uint8_t *__restrict__ bad_s, const uint8_t 
     out[k] = (uint8_t)v;
 }
 
+// Small-order part of every batch's equation, exactly.  verify_batches tests SUMS of batch equations first (one
+// equation over a range of batches, bisected on failure).  Writing E_k = P_k + T_k for the value of batch k's equation
+// (batch.rs:240-244; P_k in the prime-order subgroup, T_k in E[8]), a range sum that vanishes settles the P_k -- the
+// z_i of different batches come from different transcripts, so a non-zero P_k survives in the sum except with the
+// probability a forged signature survives batch.rs itself -- but NOT the T_k: three bits of z_i are all that multiply a
+// small-order component, and T_j + T_k = 0 happens for one input in eight (the reference's own VALIDATIONVECTORS hit
+// it).  The small-order part only depends on the scalars modulo 8:
+//     T_k = small-order part of  S_k = sum_i (z_i mod 8) R_i + sum_i ((z_i h_i mod l) mod 8) A_i,
+// (B is torsion-free) and T_k = 0 <=> [l] S_k = identity.  One group of G lanes per batch: every lane keeps the three
+// sums of the points whose scalar has bit 0 / 1 / 2 set, S = S_0 + 2 (S_1 + 2 S_2), a shuffle tree over the group,
+// then the 252 doublings of [l].  About three mixed additions per signature and one scalar multiplication per BATCH.
+__device__ __forceinline__ void ge64_shfl_down(ge64_p3 &o, const ge64_p3 &p, int d)
+{
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        o.X.v[k] = __shfl_down_sync(0xffffffffu, p.X.v[k], d); o.Y.v[k] = __shfl_down_sync(0xffffffffu, p.Y.v[k], d);
+        o.Z.v[k] = __shfl_down_sync(0xffffffffu, p.Z.v[k], d); o.T.v[k] = __shfl_down_sync(0xffffffffu, p.T.v[k], d);
+    }
+}
+
+// the group order l = 2^252 + 27742317777372353535851937790883648493 (scalar.rs constants::BASEPOINT_ORDER), low 128 bits
+__constant__ uint32_t c_l_low[4] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu};
+
+__global__ void __launch_bounds__(128)
+k_batch_torsion(const uint32_t *__restrict__ zs /* 4 words each */, const uint32_t *__restrict__ zh /* 8 words each: z_i h_i mod l */,
+                const ge_niels_packed *__restrict__ pts_R, const ge_niels_packed *__restrict__ pts_A,
+                const uint32_t *__restrict__ rep, const uint32_t *__restrict__ dense, int merged, size_t n, size_t batch,
+                size_t nbatches, uint32_t G, uint8_t *__restrict__ status)
+{
+    const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t k = gt / G;
+    const uint32_t gl = (uint32_t)(gt % G);
+    const bool live = k < nbatches;                          // dead groups run along with no signatures: the warp stays converged
+    const size_t lo = live ? k * batch : 0, hi = live ? min(n, (k + 1) * batch) : 0;
+    fe64 d2; fe64_const_2d(d2);
+    ge64_p3 S0, S1, S2;
+    ge64_identity(S0); ge64_identity(S1); ge64_identity(S2);
+    const size_t trips = (batch + G - 1) / G;                // the same trip count in every lane
+#pragma unroll 1
+    for (size_t t = 0; t < trips; t++) {
+        const size_t i = lo + t * G + gl;
+        const bool have = i < hi;
+#pragma unroll 1
+        for (int which = 0; which < 2; which++) {
+            uint32_t bits = 0;
+            ge64_niels nl;
+            if (have) {
+                const ge_niels_packed *src = which == 0 ? pts_R + i : pts_A + (merged ? (size_t)dense[rep[i]] : i);
+                bits = (which == 0 ? zs[4 * i] : zh[8 * i]) & 7u;
+                ge_niels_packed pk;
+                const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+                for (int q = 0; q < 6; q++) { uint4 v = s4[q]; pk.w[4 * q] = v.x; pk.w[4 * q + 1] = v.y; pk.w[4 * q + 2] = v.z; pk.w[4 * q + 3] = v.w; }
+                ge64_niels_unpack(nl, pk);
+            }
+            if (bits & 1u) ge64_madd(S0, S0, nl, 0u);
+            if (bits & 2u) ge64_madd(S1, S1, nl, 0u);
+            if (bits & 4u) ge64_madd(S2, S2, nl, 0u);
+        }
+    }
+    ge64_p3 S, X;
+    ge64_dbl(S, S2); ge64_add_p3(S, S, S1, d2);
+    ge64_dbl(S, S);  ge64_add_p3(S, S, S0, d2);
+    for (uint32_t d = G >> 1; d > 0; d >>= 1) { ge64_shfl_down(X, S, (int)d); ge64_add_p3(S, S, X, d2); }
+    // [l] S, left to right over the bits of l below the leading one (bits 251..128 are zero)
+    ge64_pniels Sn;
+    fe64_add(Sn.YpX, S.Y, S.X); fe64_sub(Sn.YmX, S.Y, S.X); Sn.Z = S.Z; fe64_mul(Sn.T2d, S.T, d2);
+    fe64_carry(Sn.YpX, Sn.YpX); fe64_carry(Sn.YmX, Sn.YmX);
+    ge64_p3 Q = S;
+#pragma unroll 1
+    for (int b = 251; b >= 0; b--) {
+        ge64_dbl(Q, Q);
+        if (b < 128 && ((c_l_low[b >> 5] >> (b & 31)) & 1u)) ge64_padd(Q, Q, Sn, 0u);
+    }
+    ge_p3 q; ge64_to_p3(q, Q);
+    if (live && gl == 0 && !ge_is_identity(q)) status[k] |= 8;
+}
+
+// signatures of batches that already have a verdict (malformed input or a small-order defect) leave the equations:
+// their coefficients become zero, so the range sums of verify_batches_tail only carry the undecided batches
+__global__ void k_batch_mask(const uint8_t *__restrict__ status, size_t n, size_t batch, uint32_t *__restrict__ zsprod,
+                             uint32_t *__restrict__ zh, uint32_t *__restrict__ z_R)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !status[i / batch]) return;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    uint4 *a = reinterpret_cast<uint4 *>(zsprod + 8 * i), *b = reinterpret_cast<uint4 *>(zh + 8 * i), *c = reinterpret_cast<uint4 *>(z_R + 8 * i);
+    a[0] = zero; a[1] = zero; b[0] = zero; b[1] = zero; c[0] = zero; c[1] = zero;
+}
+
 // ------------------------------------------------------------------------------------------
 // MSM inputs: scalars/points [0] = (-sum z s, B); [1 .. 1+K) = the K distinct keys (K = n without merging);
 // [1+n .. 1+2n) = (z_i, R_i).  counters: [0] running number of distinct keys, [1+p] its value after piece p, [15] = 0.
@@ -611,10 +703,13 @@ static int verify_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, int p
     return ident ? DALEK_OK : ED25519_ERR_VERIFY;
 }
 
-// Many independent batches of `batch` signatures in one call (the result of verify_batch on each): the
-// combined equation over all of them is tested first -- every batch has its own transcript, so the z_i of
-// different batches are independent and a failing batch leaves the total non-zero except with probability
-// ~2^-128 -- and only when it fails are halves re-tested down to single batches.
+// Many independent batches of `batch` signatures in one call (the result of verify_batch on each).  A batch fails iff
+// the value E_k of its equation is not the identity.  Its small-order part is tested exactly for every batch
+// (k_batch_torsion); batches that fail there, or carry malformed input, get their verdict and leave the equations
+// (k_batch_mask).  For the rest only the prime-order parts are open: the combined equation over all of them is tested
+// first -- every batch has its own transcript, so a non-zero prime-order part survives in a sum of batch equations
+// except with the probability a forgery survives batch.rs itself -- and only when it fails are halves re-tested down
+// to single batches.
 static int verify_batches_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t n, int pieces, size_t batch, int32_t *verdicts)
 {
     int rc;
@@ -623,9 +718,18 @@ static int verify_batches_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t 
     if ((rc = verify_join(ctx, b, n, pieces, &nkeys))) return rc;
     if (nb == 0) return DALEK_OK;
     if ((rc = ws_reserve(ctx, ctx->misc6, nb))) return rc;
-    k_batch_status<<<cdiv(nb, 128), 128, 0, ctx->stream>>>(b.bad_s, b.bad_r, b.bad_key, b.rep, b.dense, ctx->opt_dedupe_keys ? 1 : 0, n, batch,
+    const int merged = ctx->opt_dedupe_keys ? 1 : 0;
+    uint32_t *zh = merged ? b.hs : b.scalars + 8;            // where k_coeffs left z_i h_i
+    k_batch_status<<<cdiv(nb, 128), 128, 0, ctx->stream>>>(b.bad_s, b.bad_r, b.bad_key, b.rep, b.dense, merged, n, batch,
                                                              nb, (uint8_t *)ctx->misc6.p);
-    ctx->launches++;
+    {   // lanes per batch: enough groups to fill the machine, at least ~8 signatures per lane
+        uint32_t G = 1;
+        while (G < 32 && (size_t)G * 8 <= batch && nb * G < (size_t)ctx->sm_count * 512) G <<= 1;
+        k_batch_torsion<<<cdiv(nb * G, 128), 128, 0, ctx->stream>>>(b.zs, zh, b.points + 1 + n, b.points + 1, b.rep, b.dense, merged, n, batch,
+                                                                    nb, G, (uint8_t *)ctx->misc6.p);
+    }
+    k_batch_mask<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const uint8_t *)ctx->misc6.p, n, batch, b.zsprod, zh, b.scalars + 8 * (1 + n));
+    ctx->launches += 3;
     std::vector<uint8_t> status(nb);
     CUDA_TRY(ctx, cudaMemcpyAsync(status.data(), ctx->misc6.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -658,7 +762,7 @@ static int verify_batches_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t 
     int any = 0;
     for (size_t k = 0; k < nb; k++) {
         int v = (status[k] & 4) ? ED25519_ERR_POINT_DECOMPRESSION : (status[k] & 1) ? ED25519_ERR_SCALAR_FORMAT
-                : ((status[k] & 2) || !eq_ok[k]) ? ED25519_ERR_VERIFY : DALEK_OK;
+                : ((status[k] & (2 | 8)) || !eq_ok[k]) ? ED25519_ERR_VERIFY : DALEK_OK;
         verdicts[k] = v;
         any |= v;
     }

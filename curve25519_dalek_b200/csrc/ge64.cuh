@@ -93,6 +93,18 @@ FE_HD void ge64_dbl(ge64_p3 &r, const ge64_p3 &p)
     fe64_mul(r.T, E, Yp);                               // 3 x 2
 }
 
+// r = p + q for two extended points on the FP64 field: q -> projective Niels on the fly (edwards.rs:528-535), 9M;
+// d2 = 2d (fe64_const_2d)
+FE_HD void ge64_add_p3(ge64_p3 &r, const ge64_p3 &p, const ge64_p3 &q, const fe64 &d2)
+{
+    ge64_pniels pn;
+    fe64_add(pn.YpX, q.Y, q.X);                            // 2
+    fe64_sub(pn.YmX, q.Y, q.X);                            // 2
+    pn.Z = q.Z;
+    fe64_mul(pn.T2d, q.T, d2);
+    ge64_padd(r, p, pn, 0u);
+}
+
 FE_HD void ge64_from_p3(ge64_p3 &o, const ge_p3 &p)
 {
     fe64_from_fe(o.X, p.X); fe64_from_fe(o.Y, p.Y); fe64_from_fe(o.Z, p.Z); fe64_from_fe(o.T, p.T);

@@ -545,16 +545,6 @@ k_heavy_fixup(const uint32_t *__restrict__ heavy, const uint32_t *__restrict__ n
     }
 }
 
-// r = p + q for two extended points on the FP64 field: q -> projective Niels on the fly (edwards.rs:528-535), 9M
-__device__ __forceinline__ void ge64_add_p3(ge64_p3 &r, const ge64_p3 &p, const ge64_p3 &q, const fe64 &d2)
-{
-    ge64_pniels pn;
-    fe64_add(pn.YpX, q.Y, q.X);                            // 2
-    fe64_sub(pn.YmX, q.Y, q.X);                            // 2
-    pn.Z = q.Z;
-    fe64_mul(pn.T2d, q.T, d2);
-    ge64_padd(r, p, pn, 0u);
-}
 __device__ __forceinline__ void load_p3_f64(ge64_p3 &o, const ge_p3_raw *src)
 {
     ge_p3 q; load_p3(q, src);

@@ -125,6 +125,17 @@ def test_verify_batch_reference_fixtures(eng, oracle):
     flat, offs = _flat(msgs)
     rc, verdicts = eng.verify_batches_flat(flat, offs, b"".join(H(v["sig"]) for v in vv), b"".join(H(v["key"]) for v in vv), len(vv), 1)
     assert verdicts == [oracle.verify_batch([m], [H(v["sig"])], [H(v["key"])]) for m, v in zip(msgs, vv)]
+    # ... and as batches of 3 and of 32 (ragged tail): the small-order defects of different batches cancel in sums of
+    # batch equations one time in eight, so every batch's own small-order part has to be tested (k_batch_torsion)
+    sg, ks = [H(v["sig"]) for v in vv], [H(v["key"]) for v in vv]
+    for bs in (3, 32):
+        for dedupe in (1, 0):
+            eng.set_option("dedupe_keys", dedupe)
+            try:
+                rc, verdicts = eng.verify_batches_flat(flat, offs, b"".join(sg), b"".join(ks), len(vv), bs)
+            finally:
+                eng.set_option("dedupe_keys", 1)
+            assert verdicts == [oracle.verify_batch(msgs[k:k + bs], sg[k:k + bs], ks[k:k + bs]) for k in range(0, len(vv), bs)], (bs, dedupe)
 
 
 def test_verify_batch_python_api(eng, oracle):
