@@ -759,6 +759,14 @@ static int verify_batches_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t 
             todo.push_back({r.k0, mid, true});
         }
     }
+    {   // stage timings of the call, as in verify_tail (the first equation's bucket kernel; the R decompression of every piece)
+        float ms = 0.f;
+        if ((ms = elapsed_ms(ctx->ev_a, ctx->ev_b)) >= 0.f) ctx->last_kernel_ms = ms;
+        ctx->last_prep_ms = 0.f;
+        for (int k = 0; k < ctx->prep_pieces; k++)
+            if ((ms = elapsed_ms(ctx->ev_prep[k][0], ctx->ev_prep[k][1])) >= 0.f) ctx->last_prep_ms += ms;
+        trace_dump(ctx);
+    }
     int any = 0;
     for (size_t k = 0; k < nb; k++) {
         int v = (status[k] & 4) ? ED25519_ERR_POINT_DECOMPRESSION : (status[k] & 1) ? ED25519_ERR_SCALAR_FORMAT

@@ -289,10 +289,14 @@ int ed25519_b200_verify_batch_flat_points_dev(dalek_b200_ctx *ctx, const void *d
 /* Many independent batches in one call (2^14 batches of 256): signatures
  * [k * batch_size, min(n, (k+1) * batch_size)) form batch k and verdicts[k] receives what
  * ed25519_dalek::verify_batch (batch.rs:146-251) returns for that batch alone (0 / 1 / 3 / 4); each batch
- * uses exactly the reference's transcript (whatever "verify_chunk" is).  The combined equation over all batches is tested first
- * (independent transcripts: a failing batch leaves it non-zero except with probability ~2^-128); only
- * when it fails are halves re-tested down to single batches, so a clean call costs the same as one large
- * verify_batch, and k failing batches add about k * log2(n / batch_size) partial re-tests.
+ * uses exactly the reference's transcript (whatever "verify_chunk" is).  A batch passes iff the value E_k of its equation
+ * (batch.rs:240-250) is the identity.  The small-order part of every E_k is tested exactly, per batch (it only depends on the
+ * scalars modulo 8: S_k = sum (z_i mod 8) R_i + sum ((z_i h_i mod l) mod 8) A_i, [l] S_k == identity) -- sums of batch
+ * equations would let the small-order defects of different batches cancel, one input in eight.  For the prime-order parts the
+ * combined equation over all undecided batches is tested first (independent transcripts: a non-zero prime-order part
+ * leaves it non-zero except with the probability a forgery passes batch.rs itself, ~2^-125); only when it fails are halves
+ * re-tested down to single batches, so a clean call costs little more than one large verify_batch, and k failing batches
+ * add about k * log2(n / batch_size) partial re-tests.
  * Returns 0 if every verdict is 0, 1 otherwise, negative on engine errors.  verdicts: ceil(n / batch_size) ints (host). */
 int ed25519_b200_verify_batches_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat,
                                      const uint64_t *msg_offsets, const uint8_t *sigs,
