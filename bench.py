@@ -723,6 +723,32 @@ def physical_cores():
         return None
 
 
+def effective_cpus():
+    """CPUs this process may actually use: the affinity mask, capped by the cgroup CPU quota (the GPU boxes expose 128
+    logical CPUs behind a 16-CPU quota: more threads than that only add context switches -- tools/cpu_pool_scaling.py,
+    profiles/cpu_pool_scaling_r2.json)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = int(q) / int(per)
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except (OSError, ValueError):
+            pass
+    if quota:
+        n = max(1, min(n, int(quota + 0.5)))
+    return n, quota
+
+
 class CpuPool:
     """Persistent worker threads of the oracle (oracle/parallel.c): every thread runs the unmodified, single-threaded
     reference restatement on an independent slice.  Checker / baseline infrastructure only."""
@@ -820,7 +846,7 @@ def run_reference(args, rank, world):
     at N = 1 (2^20 pairs per step), persistent worker threads, sub-MSMs of 2^13 pairs."""
     if rank != 0:
         return None
-    threads = os.cpu_count() or 1
+    threads, quota = effective_cpus()
     steps = max(1, args.steps)
     pool = CpuPool(threads)
     vals = []
@@ -859,7 +885,8 @@ def run_reference(args, rank, world):
             "warmup": args.warmup, "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 limbs (radix 2^51), exact", "data": "synthetic", "config": config,
             "same_config_as_gpu_arm": same,
-            "cpu_baseline": {"value": val, "unit": unit, "cores": threads, "physical_cores": physical_cores(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": unit, "cores": threads, "logical_cpus": os.cpu_count(), "physical_cores": physical_cores(),
+                             "cgroup_cpu_quota": quota, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU oracle = C restatement of the reference's serial u64 backend (Rust toolchain absent: oracle/_ref cannot be built)"}
 

@@ -402,9 +402,10 @@ __global__ void k_batch_status(const uint8_t *__restrict__ bad_s, const uint8_t 
 // small-order component, and T_j + T_k = 0 happens for one input in eight (the reference's own VALIDATIONVECTORS hit
 // it).  The small-order part only depends on the scalars modulo 8:
 //     T_k = small-order part of  S_k = sum_i (z_i mod 8) R_i + sum_i ((z_i h_i mod l) mod 8) A_i,
-// (B is torsion-free) and T_k = 0 <=> [l] S_k = identity.  One group of G lanes per batch: every lane keeps the three
-// sums of the points whose scalar has bit 0 / 1 / 2 set, S = S_0 + 2 (S_1 + 2 S_2), a shuffle tree over the group,
-// then the 252 doublings of [l].  About three mixed additions per signature and one scalar multiplication per BATCH.
+// (B is torsion-free) and T_k = 0 <=> [l] S_k = identity.  One group of G lanes per batch: every lane keeps two signed
+// sums B_1, B_3 (each scalar residue mod 8 written as a + 3 b, a, b in {-1, 0, 1}), S = B_1 + 3 B_3, a shuffle tree over
+// the group (k_batch_torsion); then the 252 doublings of [l] on one thread per batch (k_batch_torsion_test).  Four mixed
+// additions per signature and one scalar multiplication per BATCH.
 __device__ __forceinline__ void ge64_shfl_down(ge64_p3 &o, const ge64_p3 &p, int d)
 {
 #pragma unroll
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(128)
 k_batch_torsion(const uint32_t *__restrict__ zs /* 4 words each */, const uint32_t *__restrict__ zh /* 8 words each: z_i h_i mod l */,
                 const ge_niels_packed *__restrict__ pts_R, const ge_niels_packed *__restrict__ pts_A,
                 const uint32_t *__restrict__ rep, const uint32_t *__restrict__ dense, int merged, size_t n, size_t batch,
-                size_t nbatches, uint32_t G, uint8_t *__restrict__ status)
+                size_t nbatches, uint32_t G, ge_p3_raw *__restrict__ sums)
 {
     const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t k = gt / G;
@@ -429,8 +430,10 @@ k_batch_torsion(const uint32_t *__restrict__ zs /* 4 words each */, const uint32
     const bool live = k < nbatches;                          // dead groups run along with no signatures: the warp stays converged
     const size_t lo = live ? k * batch : 0, hi = live ? min(n, (k + 1) * batch) : 0;
     fe64 d2; fe64_const_2d(d2);
-    ge64_p3 S0, S1, S2;
-    ge64_identity(S0); ge64_identity(S1); ge64_identity(S2);
+    // every residue k mod 8 is a + 3 b with a, b in {-1, 0, 1}: two signed accumulators, S = B1 + 3 B3, two (uniformly
+    // executed) mixed additions per point.  Any integer congruent to the scalar mod 8 gives the same small-order part.
+    ge64_p3 B1, B3;
+    ge64_identity(B1); ge64_identity(B3);
     const size_t trips = (batch + G - 1) / G;                // the same trip count in every lane
 #pragma unroll 1
     for (size_t t = 0; t < trips; t++) {
@@ -438,27 +441,56 @@ k_batch_torsion(const uint32_t *__restrict__ zs /* 4 words each */, const uint32
         const bool have = i < hi;
 #pragma unroll 1
         for (int which = 0; which < 2; which++) {
-            uint32_t bits = 0;
+            uint32_t k = 0;
             ge64_niels nl;
             if (have) {
                 const ge_niels_packed *src = which == 0 ? pts_R + i : pts_A + (merged ? (size_t)dense[rep[i]] : i);
-                bits = (which == 0 ? zs[4 * i] : zh[8 * i]) & 7u;
+                k = (which == 0 ? zs[4 * i] : zh[8 * i]) & 7u;
                 ge_niels_packed pk;
                 const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
 #pragma unroll
                 for (int q = 0; q < 6; q++) { uint4 v = s4[q]; pk.w[4 * q] = v.x; pk.w[4 * q + 1] = v.y; pk.w[4 * q + 2] = v.z; pk.w[4 * q + 3] = v.w; }
                 ge64_niels_unpack(nl, pk);
             }
-            if (bits & 1u) ge64_madd(S0, S0, nl, 0u);
-            if (bits & 2u) ge64_madd(S1, S1, nl, 0u);
-            if (bits & 4u) ge64_madd(S2, S2, nl, 0u);
+            //            k:  0  1   2  3  4   5   6   7
+            // a (weight 1):  0  1  -1  0  1   0   1  -1          k = a + 3 b (mod 8)
+            // b (weight 3):  0  0   1  1  1  -1  -1   0
+            const uint32_t a_nz = (0xd6u >> k) & 1u, a_neg = (0x84u >> k) & 1u;
+            const uint32_t b_nz = (0x7cu >> k) & 1u, b_neg = (0x60u >> k) & 1u;
+            if (a_nz) ge64_madd(B1, B1, nl, a_neg);
+            if (b_nz) ge64_madd(B3, B3, nl, b_neg);
         }
     }
     ge64_p3 S, X;
-    ge64_dbl(S, S2); ge64_add_p3(S, S, S1, d2);
-    ge64_dbl(S, S);  ge64_add_p3(S, S, S0, d2);
+    ge64_dbl(S, B3); ge64_add_p3(S, S, B3, d2); ge64_add_p3(S, S, B1, d2);     // 3 B3 + B1
     for (uint32_t d = G >> 1; d > 0; d >>= 1) { ge64_shfl_down(X, S, (int)d); ge64_add_p3(S, S, X, d2); }
-    // [l] S, left to right over the bits of l below the leading one (bits 251..128 are zero)
+    if (live && gl == 0) {
+        ge_p3 q; ge64_to_p3(q, S);
+        ge_p3_raw r; ge_p3_store_raw(r, q);
+        uint4 *o = reinterpret_cast<uint4 *>(sums + k);
+#pragma unroll
+        for (int w = 0; w < 10; w++) o[w] = make_uint4(r.w[4 * w], r.w[4 * w + 1], r.w[4 * w + 2], r.w[4 * w + 3]);
+    }
+}
+
+// [l] S_k == identity ?  One thread per batch (the lanes of k_batch_torsion would all repeat the same 252 doublings):
+// left to right over the bits of l below the leading one (bits 251..128 are zero).
+__global__ void __launch_bounds__(64)
+k_batch_torsion_test(const ge_p3_raw *__restrict__ sums, size_t nbatches, uint8_t *__restrict__ status)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nbatches) return;
+    fe64 d2; fe64_const_2d(d2);
+    ge_p3 s3;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(sums + k);
+        ge_p3_raw r;
+#pragma unroll
+        for (int w = 0; w < 10; w++) { uint4 v = src[w]; r.w[4 * w] = v.x; r.w[4 * w + 1] = v.y; r.w[4 * w + 2] = v.z; r.w[4 * w + 3] = v.w; }
+        ge_p3_load_raw(s3, r);
+    }
+    ge64_p3 S;
+    fe64_from_fe_limbs(S.X, s3.X); fe64_from_fe_limbs(S.Y, s3.Y); fe64_from_fe_limbs(S.Z, s3.Z); fe64_from_fe_limbs(S.T, s3.T);
     ge64_pniels Sn;
     fe64_add(Sn.YpX, S.Y, S.X); fe64_sub(Sn.YmX, S.Y, S.X); Sn.Z = S.Z; fe64_mul(Sn.T2d, S.T, d2);
     fe64_carry(Sn.YpX, Sn.YpX); fe64_carry(Sn.YmX, Sn.YmX);
@@ -469,7 +501,7 @@ k_batch_torsion(const uint32_t *__restrict__ zs /* 4 words each */, const uint32
         if (b < 128 && ((c_l_low[b >> 5] >> (b & 31)) & 1u)) ge64_padd(Q, Q, Sn, 0u);
     }
     ge_p3 q; ge64_to_p3(q, Q);
-    if (live && gl == 0 && !ge_is_identity(q)) status[k] |= 8;
+    if (!ge_is_identity(q)) status[k] |= 8;
 }
 
 // signatures of batches that already have a verdict (malformed input or a small-order defect) leave the equations:
@@ -725,11 +757,13 @@ static int verify_batches_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t 
     {   // lanes per batch: enough groups to fill the machine, at least ~8 signatures per lane
         uint32_t G = 1;
         while (G < 32 && (size_t)G * 8 <= batch && nb * G < (size_t)ctx->sm_count * 512) G <<= 1;
+        if ((rc = ws_reserve(ctx, ctx->red_c, nb * sizeof(ge_p3_raw)))) return rc;
         k_batch_torsion<<<cdiv(nb * G, 128), 128, 0, ctx->stream>>>(b.zs, zh, b.points + 1 + n, b.points + 1, b.rep, b.dense, merged, n, batch,
-                                                                    nb, G, (uint8_t *)ctx->misc6.p);
+                                                                    nb, G, (ge_p3_raw *)ctx->red_c.p);
+        k_batch_torsion_test<<<cdiv(nb, 64), 64, 0, ctx->stream>>>((const ge_p3_raw *)ctx->red_c.p, nb, (uint8_t *)ctx->misc6.p);
     }
     k_batch_mask<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const uint8_t *)ctx->misc6.p, n, batch, b.zsprod, zh, b.scalars + 8 * (1 + n));
-    ctx->launches += 3;
+    ctx->launches += 4;
     std::vector<uint8_t> status(nb);
     CUDA_TRY(ctx, cudaMemcpyAsync(status.data(), ctx->misc6.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -436,8 +436,11 @@ def test_verify_batch_with_key_points(eng, oracle):
         bad = bytearray(sg); bad[64 * 17 + 40] ^= 2
         assert eng.verify_batch_flat_points(flat, offs, bytes(bad), pk, pts, n) == VERIFY
         # the point is what enters the equation: a wrong point for one key fails the batch although its bytes are right
-        wrong = pts.copy(); wrong[20 * 4:20 * 5] = pts[20 * 5:20 * 6] if distinct else oracle.p3_limbs(oracle.basepoint())
-        assert eng.verify_batch_flat_points(flat, offs, sg, pk, wrong, n) == VERIFY
+        # (with repeated keys any signature of a key may lend it its point -- the contract is that all of them carry the
+        # decoding of the key's bytes -- so this is checked where every key occurs once)
+        if distinct:
+            wrong = pts.copy(); wrong[20 * 4:20 * 5] = pts[20 * 5:20 * 6]
+            assert eng.verify_batch_flat_points(flat, offs, sg, pk, wrong, n) == VERIFY
         # device-resident form
         import torch
         dev = torch.device("cuda", 0)
