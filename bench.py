@@ -305,6 +305,54 @@ def run_msm(args, rank, world, local):
     return line, eng, wl
 
 
+def run_msm_two_callers(eng, wl, local, steps=40):
+    """Throughput of a SERVICE rather than the latency of one call: two host threads, each with its own engine context on the
+    same GPU, issue blocking 2^20-pair MSM calls on the same resident inputs.  The latency-bound tail of one call (bucket
+    reduction trees, the 240 sequential doublings of the final Horner: ~0.6 ms on a handful of warps) then overlaps the other
+    call's arithmetic.  Same C-ABI entry point, same results; nothing is shared between the two contexts."""
+    import threading
+    import torch
+    import curve25519_dalek_b200 as pkg
+    eng2 = pkg.Engine(local)
+    want = wl.step_device_single()
+    engines = [eng, eng2]
+
+    def call(e):
+        rc, comp, _ = e.edwards_vartime_msm(wl.d_scalars.data_ptr(), wl.d_points.data_ptr(), wl.n, point_fmt=1, device_ptrs=True)
+        if rc != 0 or comp != want:
+            raise SystemExit("bench: two-caller MSM result differs")
+
+    for e in engines:
+        for _ in range(3):
+            call(e)
+    per = steps // 2
+    errs = []
+
+    def worker(e):
+        try:
+            torch.cuda.set_device(local)
+            for _ in range(per):
+                call(e)
+        except BaseException as ex:      # surfaced after the join
+            errs.append(ex)
+
+    torch.cuda.synchronize()
+    ts = [threading.Thread(target=worker, args=(e,)) for e in engines]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    eng2.close() if hasattr(eng2, "close") else None
+    if errs:
+        raise errs[0]
+    return {"metric": "Pippenger MSM points/sec, two concurrent callers (one engine context each) on one GPU", "value": wl.n * 2 * per / dt,
+            "unit": "points/s", "calls": 2 * per, "ms_per_call_amortised": dt / (2 * per) * 1e3, "pairs_per_call": wl.n,
+            "note": "value / ms_per_step of the main line are ONE caller's blocking calls; this leg shows what overlapping the tail of one call with the next call's arithmetic yields"}
+
+
 def run_msm_like_for_like(eng, n, steps):
     """The N = 1 rate at the per-GPU size of the N > 1 runs (2^21 pairs): the like-for-like denominator of the scaling
     efficiency.  Device-resident, same call as the headline."""
@@ -355,7 +403,7 @@ def build_verify_inputs(eng, n, nkeys=1024):
     return flat, offs, np.frombuffer(sigs, dtype=np.uint8).copy(), np.frombuffer(pks, dtype=np.uint8).copy()
 
 
-def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkeys=1024, batch_size=None, each=False):
+def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkeys=1024, batch_size=None, each=False, key_points=False):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -377,6 +425,15 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
     h = [torch.from_numpy(x if x.dtype == np.uint8 else x.view(np.int64)).pin_memory() for x in (flat, offs, sigs, pks)]
     d = [x.to(dev) for x in h]
     torch.cuda.synchronize()
+    if key_points:
+        # what a Rust caller holds: the VerifyingKeys' decompressed points (E/verifying.rs:65-71), made here once with the
+        # batch codec, outside the timed region -- as VerifyingKey::from_bytes is outside verify_batch in the reference
+        rc_k, limbs, okk = eng.decompress_batch(pks.tobytes(), n)
+        if rc_k != 0 or not all(okk):
+            raise SystemExit("bench: key decompression failed")
+        hk = torch.from_numpy(np.frombuffer(limbs, dtype=np.uint64).copy().view(np.int64)).pin_memory()
+        dk = hk.to(dev)
+        torch.cuda.synchronize()
 
     each_res = np.zeros(n, dtype=np.uint8) if each else None
     # One call over n = 2^22 signatures: the reference's single Merlin transcript is a strictly sequential sponge of
@@ -393,6 +450,12 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
             rc = fn(eng.h, b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(), n, 0, each_res.ctypes.data)
             if rc != 0:
                 raise SystemExit("bench: verify_each rejected valid signatures (rc=%d)" % rc)
+            return
+        if batch_size and key_points:
+            rc, verdicts = eng.verify_batches_flat_points(b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(),
+                                                          (hk if host else dk).data_ptr(), n, batch_size, device_ptrs=not host)
+            if rc != 0 or any(verdicts):
+                raise SystemExit("bench: verify_batches (key points) rejected valid signatures")
             return
         if batch_size:      # independent batches of `batch_size`, one verdict each
             rc, verdicts = eng.verify_batches_flat(b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(), n, batch_size,
@@ -498,14 +561,15 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
         "config": {"workload": "ed25519_verify_batch", "signatures_per_gpu": n, "message_bytes": 59, "distinct_keys": min(nkeys, n),
                    "transcript": ("one Merlin transcript per %d signatures (option verify_chunk, opt-in; default = the reference's single transcript)" % transcript_chunk)
                                  if transcript_chunk else "the reference's transcripts (one per batch)",
-                   "keys": "32-byte encodings, decompressed inside the call",
+                   "keys": "the callers' decompressed points (VerifyingKey, 160 B each) beside the 32-byte encodings" if key_points
+                           else "32-byte encodings, decompressed inside the call",
                    "batch_size": batch_size or None,
                    "timing": "value / ms_per_step: K blocking C-ABI calls bracketed by barrier + device sync, max over ranks; "
                              "device_ms_per_step: CUDA events on the engine's stream around each call (rank 0)",
                    "device_ms_per_step": statistics.mean(call_ms), "e2e_device_ms_per_step": statistics.mean(e2e_call_ms),
                    "l2": "inputs (%.0f MB) exceed the 126 MB L2" % (n * 155 / 1e6),
                    "replicas": "independent batches per GPU, no collective" if world > 1 else "single batch"},
-        "e2e": {"value": n * world * steps / et, "unit": "sigs/s", "h2d_bytes_per_step": n * 155 + (n + 1) * 8,
+        "e2e": {"value": n * world * steps / et, "unit": "sigs/s", "h2d_bytes_per_step": n * 155 + (n + 1) * 8 + (n * 160 if key_points else 0),
                 "d2h_bytes_per_step": n if each else (4 * ((n + batch_size - 1) // batch_size) if batch_size else 192)},
         "gpu_launches": int(launches),
         "roofline": dominant or {"bound": "hbm", "kernel": "whole call (155 B per signature)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -932,6 +996,7 @@ def main():
                 line["verify_batch"] = {k: v[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "e2e", "config", "gpu_launches", "roofline")}
         if not args.no_extras and world == 1:
             line["msm_2p21_pairs"] = run_msm_like_for_like(eng, 1 << 21, min(args.steps, 20))
+            line["msm_two_callers"] = run_msm_two_callers(eng, wl, local, min(2 * args.steps, 60))
             line["msm_compressed_input"] = run_msm_compressed(eng, wl)
             line["small_msm_latency"] = run_small_latency(eng)
             line["msm_precomputed"] = run_precomputed(eng, wl)
@@ -942,6 +1007,9 @@ def main():
             # the same with every public key different (no key de-duplication possible)
             v2 = run_verify(args, rank, world, local, eng=eng, steps=3, warmup=3, nkeys=1 << 30)
             line["verify_batch"]["all_distinct_keys"] = {k: v2[k] for k in ("value", "unit", "ms_per_step", "e2e")}
+            # ... and with the VerifyingKeys' points passed in, as the reference's verify_batch receives them (batch.rs:236-238)
+            v2p = run_verify(args, rank, world, local, eng=eng, steps=3, warmup=3, nkeys=1 << 30, key_points=True)
+            line["verify_batch"]["all_distinct_keys_with_key_points"] = {k: v2p[k] for k in ("value", "unit", "ms_per_step", "e2e")}
             # ONE verdict over all 2^22 signatures with the opt-in chunked transcript (NOT reference-equivalent on inputs
             # with small-order components: include/dalek_b200.h)
             v3 = run_verify(args, rank, world, local, eng=eng, steps=3, warmup=3, batch_size=0)

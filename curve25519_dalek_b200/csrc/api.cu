@@ -31,6 +31,7 @@ int dalek_b200_init(int device, dalek_b200_ctx **out)
         cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->stream_hash, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_call0) != cudaSuccess || cudaEventCreate(&ctx->ev_call1) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -40,7 +41,8 @@ int dalek_b200_init(int device, dalek_b200_ctx **out)
         return DALEK_E_CUDA;
     }
     for (int i = 0; i < 8; i++)
-        if (cudaEventCreateWithFlags(&ctx->ev_grp[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&ctx->ev_prep[i][0]) != cudaSuccess ||
+        if (cudaEventCreateWithFlags(&ctx->ev_grp[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_hram[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&ctx->ev_prep[i][0]) != cudaSuccess ||
             cudaEventCreate(&ctx->ev_prep[i][1]) != cudaSuccess) { delete ctx; return DALEK_E_CUDA; }
     *out = ctx;
     return DALEK_OK;
@@ -53,6 +55,7 @@ void dalek_b200_destroy(dalek_b200_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->stream2);
     cudaStreamSynchronize(ctx->stream3);
+    cudaStreamSynchronize(ctx->stream_hash);
     DevBuf *bufs[] = {&ctx->scalars, &ctx->points_in, &ctx->points, &ctx->digits, &ctx->counts, &ctx->offsets,
                       &ctx->sorted, &ctx->buckets, &ctx->red_a, &ctx->red_b, &ctx->red_c, &ctx->red_d, &ctx->key_pts,
                       &ctx->result, &ctx->flags, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->misc3,
@@ -61,7 +64,8 @@ void dalek_b200_destroy(dalek_b200_ctx *ctx)
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     cudaEventDestroy(ctx->ev_join2); cudaEventDestroy(ctx->ev_call0); cudaEventDestroy(ctx->ev_call1);
-    for (int i = 0; i < 8; i++) { cudaEventDestroy(ctx->ev_grp[i]); cudaEventDestroy(ctx->ev_prep[i][0]); cudaEventDestroy(ctx->ev_prep[i][1]); }
+    for (int i = 0; i < 8; i++) { cudaEventDestroy(ctx->ev_grp[i]); cudaEventDestroy(ctx->ev_hram[i]); cudaEventDestroy(ctx->ev_prep[i][0]); cudaEventDestroy(ctx->ev_prep[i][1]); }
+    cudaStreamDestroy(ctx->stream_hash);
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2); cudaStreamDestroy(ctx->stream_copy); cudaStreamDestroy(ctx->stream3);
     delete ctx;
 }
@@ -80,6 +84,7 @@ int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value)
     if (!strcmp(name, "dedupe_keys")) { ctx->opt_dedupe_keys = value ? 1 : 0; return 0; }
     if (!strcmp(name, "verify_pieces")) { if (value < 1 || value > 8) return DALEK_E_INVALID_ARG; ctx->opt_verify_pieces = value; return 0; }
     if (!strcmp(name, "transcript_warp")) { ctx->opt_transcript_warp = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "transcript_blocks")) { ctx->opt_transcript_blocks = value ? 1 : 0; return 0; }
     if (!strcmp(name, "small_straus")) { ctx->opt_small_straus = value ? 1 : 0; return 0; }
     if (!strcmp(name, "acc_tma")) { ctx->opt_acc_tma = value ? 1 : 0; return 0; }
     if (!strcmp(name, "field_f64")) { ctx->opt_field_f64 = value ? 1 : 0; return 0; }

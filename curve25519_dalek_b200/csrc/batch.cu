@@ -107,6 +107,89 @@ k_transcript_warp(const uint32_t *__restrict__ hrams, const uint32_t *__restrict
     merlin_zs_warp(hrams + 16 * lo, sigs + 16 * lo, hi - lo, zs + 4 * lo);
 }
 
+// One thread per transcript again (many transcripts: throughput-bound), without per-byte work on the sponge state: the
+// absorbed bytes of the current 166-byte rate block are first laid out in a per-thread shared-memory buffer (byte, 16-bit
+// or 32-bit stores, whatever the block position allows; the 43-word stride keeps a warp's lock-step stores on 32 different
+// banks), then XORed into the state 64 bits at a time with static indices, so the 25 state words never need dynamic
+// addressing.  The transcript starts from the constant state after Transcript::new (MERLIN_PREFIX_*, transcript_warp.cuh)
+// and the challenge phase (meta_ad + prf per signature) only ever touches bytes 16..41 and 167 of the block: static too.
+// Same byte stream as k_transcript (hash.cuh's strobe_* functions), checked against it and the oracle in the tests.
+#define TB_WORDS 43u
+__global__ void __launch_bounds__(64)
+k_transcript_blocks(const uint32_t *__restrict__ hrams, const uint32_t *__restrict__ sigs, size_t n, uint32_t chunk, uint32_t *__restrict__ zs)
+{
+    __shared__ uint32_t s_buf[64 * TB_WORDS];
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t lo = t * chunk;
+    if (lo >= n) return;
+    const size_t hi = min(lo + (size_t)chunk, n);
+    uint32_t *bw = s_buf + TB_WORDS * threadIdx.x;
+    uint8_t *bb = reinterpret_cast<uint8_t *>(bw);
+    uint16_t *bh = reinterpret_cast<uint16_t *>(bw);
+#pragma unroll
+    for (uint32_t w = 0; w < 42; w++) bw[w] = 0;
+    uint64_t st[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) st[i] = merlin_prefix_lane((uint32_t)i);
+    uint32_t pos = MERLIN_PREFIX_POS, pos_begin = MERLIN_PREFIX_POS_BEGIN;
+    auto run_f = [&]() {                                                // strobe_run_f with the block's bytes still in the buffer
+        bb[pos] ^= (uint8_t)pos_begin; bb[pos + 1] ^= 0x04; bb[STROBE_R + 1] ^= 0x80;
+#pragma unroll
+        for (int w = 0; w < 21; w++) { st[w] ^= (uint64_t)bw[2 * w] | ((uint64_t)bw[2 * w + 1] << 32); bw[2 * w] = 0; bw[2 * w + 1] = 0; }
+        keccak_f1600(st);
+        pos = 0; pos_begin = 0;
+    };
+    auto put = [&](uint32_t v) { bb[pos] = (uint8_t)v; if (++pos == STROBE_R) run_f(); };
+    auto put_word = [&](uint32_t w) {                                   // four data bytes, little-endian
+        if (pos + 4 < STROBE_R && (pos & 1) == 0) {                     // stays inside the block (166 = 2 mod 4: never ends exactly on it)
+            if (pos & 2) { bh[pos >> 1] = (uint16_t)w; bh[(pos >> 1) + 1] = (uint16_t)(w >> 16); } else bw[pos >> 2] = w;
+            pos += 4;
+        } else {
+            put(w & 0xff); put((w >> 8) & 0xff); put((w >> 16) & 0xff); put(w >> 24);
+        }
+    };
+    auto begin_op = [&](uint32_t flags) { const uint32_t old = pos_begin; pos_begin = pos + 1; put(old); put(flags); };
+    // (every put site carries an inlined copy of run_f: large code, but measured faster than one shared out-of-line copy)
+    for (size_t i = lo; i < hi; i++) {                                  // append_message(b"hram", ..)  batch.rs:195-197
+        begin_op(SFLAG_M | SFLAG_A);
+        put('h'); put('r'); put('a'); put('m'); put(64); put(0); put(0); put(0);
+        begin_op(SFLAG_A);
+        const uint4 *src = reinterpret_cast<const uint4 *>(hrams + 16 * i);
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) { const uint4 v = src[q]; put_word(v.x); put_word(v.y); put_word(v.z); put_word(v.w); }
+    }
+    for (size_t i = lo; i < hi; i++) {                                  // append_message(b"sig.s", ..)  batch.rs:199-201
+        begin_op(SFLAG_M | SFLAG_A);
+        put('s'); put('i'); put('g'); put('.'); put('s'); put(32); put(0); put(0); put(0);
+        begin_op(SFLAG_A);
+        const uint4 *src = reinterpret_cast<const uint4 *>(sigs + 16 * i + 8);
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) { const uint4 v = src[q]; put_word(v.x); put_word(v.y); put_word(v.z); put_word(v.w); }
+    }
+    // build_rng().finalize(&mut ZeroRng): meta_ad("rng"), KEY(32 zero bytes)  (transcript.rs:157-173)
+    begin_op(SFLAG_M | SFLAG_A);
+    put('r'); put('n'); put('g');
+    begin_op(SFLAG_A | SFLAG_C);
+    if (pos != 0) run_f();
+    st[0] = 0; st[1] = 0; st[2] = 0; st[3] = 0;                         // KEY overwrites state bytes 0..31; pos = 32
+    // per signature: meta_ad(16u32), prf(16)  (transcript.rs:200-206).  Block bytes P..P+7 = 0, 0x12, 16, 0, 0, 0, P+1, 0x07,
+    // run_f at P+8 (st[P+8] ^= P+7, st[P+9] ^= 0x04, st[167] ^= 0x80); P = 32 for the first draw, 16 afterwards
+    bool first = true;
+#pragma unroll 1
+    for (size_t i = lo; i < hi; i++) {
+        const uint32_t P = first ? 32u : 16u;
+        const uint64_t w0 = ((uint64_t)0x12 << 8) | ((uint64_t)16 << 16) | ((uint64_t)(P + 1) << 48) | ((uint64_t)0x07 << 56);
+        const uint64_t w1 = (uint64_t)(P + 7) | ((uint64_t)0x04 << 8);
+        if (first) { st[4] ^= w0; st[5] ^= w1; } else { st[2] ^= w0; st[3] ^= w1; }
+        st[20] ^= (uint64_t)0x80 << 56;
+        keccak_f1600(st);
+        zs[4 * i] = (uint32_t)st[0]; zs[4 * i + 1] = (uint32_t)(st[0] >> 32);
+        zs[4 * i + 2] = (uint32_t)st[1]; zs[4 * i + 3] = (uint32_t)(st[1] >> 32);
+        st[0] = 0; st[1] = 0;
+        first = false;
+    }
+}
+
 #define TRANSCRIPT_WARP_MAX 2048          // up to this many transcripts per launch: one warp each
 static void launch_transcripts(dalek_b200_ctx *ctx, cudaStream_t st, const uint32_t *hrams, const uint32_t *sigs, size_t cnt, uint32_t chunk,
                                uint32_t *zs)
@@ -114,6 +197,8 @@ static void launch_transcripts(dalek_b200_ctx *ctx, cudaStream_t st, const uint3
     const size_t ntr = (cnt + chunk - 1) / chunk;
     if (ntr <= TRANSCRIPT_WARP_MAX && ctx->opt_transcript_warp)
         k_transcript_warp<<<(unsigned)ntr, 32, 0, st>>>(hrams, sigs, cnt, chunk, zs);
+    else if (ctx->opt_transcript_blocks)
+        k_transcript_blocks<<<cdiv(ntr, 64), 64, 0, st>>>(hrams, sigs, cnt, chunk, zs);
     else
         k_transcript<<<cdiv(ntr, 64), 64, 0, st>>>(hrams, sigs, cnt, chunk, zs);
     ctx->launches++;
@@ -555,29 +640,32 @@ static int verify_reserve(dalek_b200_ctx *ctx, size_t n, VerifyBufs &b)
     return 0;
 }
 
-// Front end for signatures [i0, i1) (i0 a multiple of verify_chunk): hashing, transcript, coefficients on a
-// high-priority stream (the main one for even pieces, stream3 for odd ones: a transcript kernel is a
+// Front end for signatures [i0, i1) (i0 a multiple of verify_chunk): hashing on stream_hash; transcript and coefficients
+// on a high-priority stream (the main one for even pieces, stream3 for odd ones: a transcript kernel is a
 // latency-bound chain of Keccak permutations on few warps, so consecutive pieces should overlap);
 // decompression on the low-priority stream.  All wait for `ready` if given.
 static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t *d_msgs, const uint64_t *d_offs,
                         const uint32_t *d_sigs, const uint32_t *d_keys, size_t n, size_t i0, size_t i1, cudaEvent_t ready,
                         int piece = 0)
 {
-    cudaStream_t st = (piece & 1) ? ctx->stream3 : ctx->stream, st2 = ctx->stream2;
+    cudaStream_t st = (piece & 1) ? ctx->stream3 : ctx->stream, st2 = ctx->stream2, sh = ctx->stream_hash;
     const size_t cnt = i1 - i0;
     // verify_chunk = 0 (default): ONE transcript over the whole batch, the reference's (batch.rs:168-222); it needs every
     // hram first, so it runs in verify_whole_transcript after the last piece.  > 0: one transcript per chunk (opt-in).
     const uint32_t chunk = (uint32_t)ctx->opt_verify_chunk;
-    if (ready) { CUDA_TRY(ctx, cudaStreamWaitEvent(st, ready, 0)); CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ready, 0)); }
+    if (ready) { CUDA_TRY(ctx, cudaStreamWaitEvent(sh, ready, 0)); CUDA_TRY(ctx, cudaStreamWaitEvent(st2, ready, 0)); }
     if (cnt) {
-        // the hashing -> transcript chain has little parallelism in its second stage: enqueue it first
-        k_hram<<<cdiv(cnt, 128), 128, 0, st>>>(d_msgs, d_offs + i0, d_sigs + 16 * i0, d_keys + 8 * i0, cnt, b.hrams + 16 * i0,
+        // the hashing -> transcript chain has little parallelism in its second stage: enqueue it first.  SHA-512 of every
+        // piece runs on its own stream, so the hashing of piece k+2 is not queued behind the transcripts of piece k
+        k_hram<<<cdiv(cnt, 128), 128, 0, sh>>>(d_msgs, d_offs + i0, d_sigs + 16 * i0, d_keys + 8 * i0, cnt, b.hrams + 16 * i0,
                                                b.hs + 8 * i0, b.flags, b.bad_s + i0);
         ctx->launches++;
-        trace_mark(ctx, "hram done (hash stream)", st);
+        trace_mark(ctx, "hram done (hash stream)", sh);
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_hram[piece & 7], sh));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_hram[piece & 7], 0));
         if (chunk) {
             launch_transcripts(ctx, st, b.hrams + 16 * i0, d_sigs + 16 * i0, cnt, chunk, b.zs + 4 * i0);
-            trace_mark(ctx, "transcript done (hash stream)", st);
+            trace_mark(ctx, "transcript done (transcript stream)", st);
         }
     }
     ge_niels_packed *points_A = b.points + 1;
@@ -611,7 +699,7 @@ static int verify_front(dalek_b200_ctx *ctx, const VerifyBufs &b, const uint8_t 
         k_coeffs<<<cdiv(cnt, 128), 128, 0, st>>>(b.zs + 4 * i0, d_sigs + 16 * i0, b.hs + 8 * i0, cnt, b.scalars + 8 * (1 + n + i0),
                                                  out_zh, b.zsprod + 8 * i0);
         ctx->launches++;
-        trace_mark(ctx, "coeffs done (hash stream)", st);
+        trace_mark(ctx, "coeffs done (transcript stream)", st);
     }
     trace_mark(ctx, "keys done (decompress stream)", st2);
     CUDA_TRY(ctx, cudaGetLastError());
@@ -625,7 +713,7 @@ static int verify_whole_transcript(dalek_b200_ctx *ctx, const VerifyBufs &b, con
 {
     if (ctx->opt_verify_chunk || !n) return 0;
     cudaStream_t st = ctx->stream;
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join2, ctx->stream3));           // odd pieces hash on stream3
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join2, ctx->stream_hash));       // every piece is hashed on stream_hash
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join2, 0));
     launch_transcripts(ctx, st, b.hrams, d_sigs, n, (uint32_t)std::min<size_t>(n, 0xffffffffu), b.zs);
     trace_mark(ctx, "whole-batch transcript done (hash stream)", st);
@@ -888,6 +976,27 @@ int ed25519_b200_verify_batches_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_fl
     if (!ctx || !batch_size || batch_size > (1u << 20) || (n && (!msg_offsets || !sigs || !pubkeys || !verdicts))) return DALEK_E_INVALID_ARG;
     ChunkOverride guard(ctx, batch_size);
     return verify_host(ctx, msgs_flat, msg_offsets, sigs, pubkeys, n, batch_size, verdicts);
+}
+
+int ed25519_b200_verify_batches_flat_points_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat, const void *d_msg_offsets, const void *d_sigs,
+                                                const void *d_pubkeys, const void *d_key_points, size_t n, size_t batch_size, int32_t *verdicts)
+{
+    if (!ctx || !batch_size || batch_size > (1u << 20) || (n && (!d_msg_offsets || !d_sigs || !d_pubkeys || !d_key_points || !verdicts)))
+        return DALEK_E_INVALID_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ChunkOverride guard(ctx, batch_size);
+    KeyPointsGuard kp(ctx, (const uint64_t *)d_key_points);
+    return verify_dev(ctx, (const uint8_t *)d_msgs_flat, (const uint64_t *)d_msg_offsets, (const uint32_t *)d_sigs,
+                      (const uint32_t *)d_pubkeys, n, batch_size, verdicts);
+}
+
+int ed25519_b200_verify_batches_flat_points(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint64_t *msg_offsets, const uint8_t *sigs,
+                                            const uint8_t *pubkeys, const uint64_t *key_points, size_t n, size_t batch_size, int32_t *verdicts)
+{
+    if (!ctx || !batch_size || batch_size > (1u << 20) || (n && (!msg_offsets || !sigs || !pubkeys || !key_points || !verdicts)))
+        return DALEK_E_INVALID_ARG;
+    ChunkOverride guard(ctx, batch_size);
+    return verify_host(ctx, msgs_flat, msg_offsets, sigs, pubkeys, n, batch_size, verdicts, key_points);
 }
 
 int ed25519_b200_verify_batch_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint64_t *msg_offsets,

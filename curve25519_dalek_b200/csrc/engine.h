@@ -22,7 +22,9 @@ struct dalek_b200_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;
     cudaStream_t stream_copy = nullptr;
-    cudaStream_t stream3 = nullptr;      // second hashing/transcript chain (odd verify pieces)
+    cudaStream_t stream3 = nullptr;      // second transcript chain (odd verify pieces)
+    cudaStream_t stream_hash = nullptr;  // SHA-512 of every verify piece: never queued behind a transcript (a long dependent chain)
+    cudaEvent_t ev_hram[8] = {};         // "hram of piece k done" (stream_hash)
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;   // device span of the last hot-path call (CallTimer)
     cudaEvent_t ev_prep[8][2] = {};      // around the R-decompression kernel of each verify_batch piece (stream2)
@@ -43,6 +45,7 @@ struct dalek_b200_ctx {
     long opt_decompress_f64 = 1; // square-root exponentiation of point decompression on the FP64-pipe field
     long opt_acc_tma = 0;       // bucket kernel gathers points with TMA bulk copies + mbarriers instead of cp.async (A/B option)
     long opt_transcript_warp = 1; // up to 2048 Merlin transcripts per launch run one WARP each (25-lane Keccak); 0 = one thread each
+    long opt_transcript_blocks = 1; // more transcripts than that: one THREAD each with the rate block staged in shared memory (0 = byte-wise sponge)
     long opt_small_straus = 1;  // fewer than 190 pairs: vartime Straus (3 launches) instead of the bucket pipeline
     long opt_field_f64 = 1;     // bucket kernel on the FP64 pipe (fe64.cuh) instead of IMAD.WIDE (fe.cuh)
     // timing of the dominant kernel in the last call

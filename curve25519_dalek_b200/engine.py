@@ -67,6 +67,8 @@ def load_library():
     lib.ed25519_b200_verify_batches_flat.argtypes = [vp, vp, vp, vp, vp, sz, sz, vp]
     lib.ed25519_b200_verify_batch_flat_points.argtypes = [vp, vp, vp, vp, vp, vp, sz]
     lib.ed25519_b200_verify_batch_flat_points_dev.argtypes = [vp, vp, vp, vp, vp, vp, sz]
+    lib.ed25519_b200_verify_batches_flat_points.argtypes = [vp, vp, vp, vp, vp, vp, sz, sz, vp]
+    lib.ed25519_b200_verify_batches_flat_points_dev.argtypes = [vp, vp, vp, vp, vp, vp, sz, sz, vp]
     lib.ed25519_b200_verify_batches_flat_dev.argtypes = [vp, vp, vp, vp, vp, sz, sz, vp]
     lib.dalek_b200_precomp_new.argtypes = [vp, vp, C.c_int, sz, C.POINTER(vp)]
     lib.dalek_b200_precomp_len.argtypes = [vp]
@@ -316,6 +318,14 @@ class Engine:
         verdicts = (C.c_int32 * max(nb, 1))()
         fn = self.lib.ed25519_b200_verify_batches_flat_dev if device_ptrs else self.lib.ed25519_b200_verify_batches_flat
         rc = self._check(fn(self.h, _ptr(msgs_flat), _ptr(offsets), _ptr(sigs), _ptr(pubkeys), n, batch_size, C.addressof(verdicts)))
+        return rc, list(verdicts)[:nb]
+
+    def verify_batches_flat_points(self, msgs_flat, offsets, sigs, pubkeys, key_points, n, batch_size, device_ptrs=False):
+        """verify_batches_flat for callers holding VerifyingKeys (key_points = n x 20 u64 limbs): no key decompression."""
+        nb = (n + batch_size - 1) // batch_size
+        verdicts = (C.c_int32 * max(nb, 1))()
+        fn = self.lib.ed25519_b200_verify_batches_flat_points_dev if device_ptrs else self.lib.ed25519_b200_verify_batches_flat_points
+        rc = self._check(fn(self.h, _ptr(msgs_flat), _ptr(offsets), _ptr(sigs), _ptr(pubkeys), _ptr(key_points), n, batch_size, C.addressof(verdicts)))
         return rc, list(verdicts)[:nb]
 
     def verify_each_flat(self, msgs_flat, offsets, sigs, pubkeys, n, strict=False, device_ptrs=False):

@@ -68,7 +68,9 @@ const char *dalek_b200_last_error(const dalek_b200_ctx *ctx);
  * "dedupe_keys" (1 = decompress every distinct public key once and give it one MSM term, default), "double_base_comb" (1 =
  * fixed-base comb for double-base batches of >= 4096 pairs, default), "precomp_tables" (1 = precomputations of >= 4096 points
  * also keep the 2^(cw) P window tables; default 0: measured, the 1.7 GB of randomly gathered table entries cost the bucket
- * kernel what the shorter tail saves), "trace" (1 = per-stage device timeline of verify_batch on stderr).
+ * kernel what the shorter tail saves), "transcript_warp" (1 = launches of up to 2048 Merlin transcripts run one warp each,
+ * default), "transcript_blocks" (1 = larger launches run one thread per transcript with the rate block staged in shared
+ * memory, default; 0 = byte-wise sponge), "trace" (1 = per-stage device timeline of verify_batch on stderr).
  * Returns 0 or DALEK_E_INVALID_ARG. */
 int dalek_b200_set_option(dalek_b200_ctx *ctx, const char *name, long value);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
@@ -304,6 +306,14 @@ int ed25519_b200_verify_batches_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_fl
 int ed25519_b200_verify_batches_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat,
                                          const void *d_msg_offsets, const void *d_sigs,
                                          const void *d_pubkeys, size_t n, size_t batch_size, int32_t *verdicts);
+/* The same for callers that hold VerifyingKeys (the reference's bench shape, E/benches/ed25519_benchmarks.rs:56-73: every key
+ * different): key_points as in ed25519_b200_verify_batch_flat_points -- no key is decompressed inside the call (batch.rs:236-238). */
+int ed25519_b200_verify_batches_flat_points(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint64_t *msg_offsets,
+                                            const uint8_t *sigs, const uint8_t *pubkeys, const uint64_t *key_points, size_t n,
+                                            size_t batch_size, int32_t *verdicts);
+int ed25519_b200_verify_batches_flat_points_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat, const void *d_msg_offsets,
+                                                const void *d_sigs, const void *d_pubkeys, const void *d_key_points, size_t n,
+                                                size_t batch_size, int32_t *verdicts);
 /* Many independent single verifications: results[i] = what VerifyingKey::from_bytes followed by
  * verify (strict = 0, E/verifying.rs:167-175, :203-219) or verify_strict (strict = 1, E/verifying.rs:359-382)
  * returns for signature i alone: 0 Ok, 1 Verify, 3 ScalarFormat, 4 PointDecompression.  R' = [s]B - [k]A is

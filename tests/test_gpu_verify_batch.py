@@ -64,19 +64,23 @@ def test_transcript_kernels_agree(eng, oracle):
     """The Merlin transcript runs on one WARP (25-lane Keccak, csrc/transcript_warp.cuh) when a launch has few transcripts
     and on one thread per transcript otherwise; option `transcript_warp` selects.  Both must draw the oracle's z_i: one
     transcript over 301 signatures (n = 53 and 219 end exactly on a rate-block boundary), and chunks of 7."""
-    for n in (53, 219, 301):
+    for n in (1, 2, 53, 219, 301):
         msgs, sigs, pks = make_batch(oracle, n, seed=5000 + n, msg_len=33)
         for chunk in (0, 7):
             rc_o, zs_o = oracle.verify_batch(msgs, sigs, pks, chunk=chunk, want_zs=True)
             assert rc_o == OK
-            for warp in (1, 0):
+            # warp = 1: one warp per transcript; warp = 0: one thread each, with the rate block staged in shared memory
+            # (blocks = 1, k_transcript_blocks) or byte by byte on the sponge state (blocks = 0, k_transcript)
+            for warp, blocks in ((1, 1), (0, 1), (0, 0)):
                 eng.set_option("transcript_warp", warp)
+                eng.set_option("transcript_blocks", blocks)
                 eng.set_option("verify_chunk", chunk)
                 try:
                     assert run(eng, msgs, sigs, pks) == OK
-                    assert eng.last_zs(n) == zs_o, (n, chunk, warp)
+                    assert eng.last_zs(n) == zs_o, (n, chunk, warp, blocks)
                 finally:
                     eng.set_option("transcript_warp", 1)
+                    eng.set_option("transcript_blocks", 1)
                     eng.set_option("verify_chunk", 0)
 
 
@@ -448,3 +452,11 @@ def test_verify_batch_with_key_points(eng, oracle):
              for x in (flat, offs, np.frombuffer(sg, dtype=np.uint8).copy(), np.frombuffer(pk, dtype=np.uint8).copy(), pts)]
         assert eng.verify_batch_flat_points(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), d[4].data_ptr(), n,
                                             device_ptrs=True) == OK
+        # independent batches of 16 with the callers' points: each verdict is the reference's for that batch alone
+        want = [oracle.verify_batch(msgs[k:k + 16], [bytes(bad[64 * i:64 * i + 64]) for i in range(k, min(n, k + 16))], pks[k:k + 16])
+                for k in range(0, n, 16)]
+        assert VERIFY in want and OK in want
+        assert eng.verify_batches_flat_points(flat, offs, bytes(bad), pk, pts, n, 16) == (1, want)
+        dbad = torch.from_numpy(np.frombuffer(bytes(bad), dtype=np.uint8).copy()).to(dev)
+        assert eng.verify_batches_flat_points(d[0].data_ptr(), d[1].data_ptr(), dbad.data_ptr(), d[3].data_ptr(), d[4].data_ptr(), n, 16,
+                                              device_ptrs=True) == (1, want)
