@@ -840,26 +840,45 @@ static int verify_batches_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t 
     if ((rc = ws_reserve(ctx, ctx->misc6, nb))) return rc;
     const int merged = ctx->opt_dedupe_keys ? 1 : 0;
     uint32_t *zh = merged ? b.hs : b.scalars + 8;            // where k_coeffs left z_i h_i
-    k_batch_status<<<cdiv(nb, 128), 128, 0, ctx->stream>>>(b.bad_s, b.bad_r, b.bad_key, b.rep, b.dense, merged, n, batch,
-                                                             nb, (uint8_t *)ctx->misc6.p);
+    // The per-batch status (malformed input, small-order defect) is computed on the decompression stream, idle by now, WHILE
+    // the main stream evaluates the combined equation over everything.  If that equation holds, every prime-order part is
+    // settled and the verdicts follow from the status alone -- the common case costs no serial time for the status kernels
+    // (the [l] S_k chains are latency-bound and hide under the bucket kernel).  If it fails, the batches that already have a
+    // verdict are masked out of the coefficients and the ranges are examined as before.
+    cudaStream_t ss = ctx->stream2;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
+    k_batch_status<<<cdiv(nb, 128), 128, 0, ss>>>(b.bad_s, b.bad_r, b.bad_key, b.rep, b.dense, merged, n, batch, nb, (uint8_t *)ctx->misc6.p);
     {   // lanes per batch: enough groups to fill the machine, at least ~8 signatures per lane
         uint32_t G = 1;
         while (G < 32 && (size_t)G * 8 <= batch && nb * G < (size_t)ctx->sm_count * 512) G <<= 1;
         if ((rc = ws_reserve(ctx, ctx->red_c, nb * sizeof(ge_p3_raw)))) return rc;
-        k_batch_torsion<<<cdiv(nb * G, 128), 128, 0, ctx->stream>>>(b.zs, zh, b.points + 1 + n, b.points + 1, b.rep, b.dense, merged, n, batch,
-                                                                    nb, G, (ge_p3_raw *)ctx->red_c.p);
-        k_batch_torsion_test<<<cdiv(nb, 64), 64, 0, ctx->stream>>>((const ge_p3_raw *)ctx->red_c.p, nb, (uint8_t *)ctx->misc6.p);
+        k_batch_torsion<<<cdiv(nb * G, 128), 128, 0, ss>>>(b.zs, zh, b.points + 1 + n, b.points + 1, b.rep, b.dense, merged, n, batch,
+                                                           nb, G, (ge_p3_raw *)ctx->red_c.p);
+        k_batch_torsion_test<<<cdiv(nb, 64), 64, 0, ss>>>((const ge_p3_raw *)ctx->red_c.p, nb, (uint8_t *)ctx->misc6.p);
     }
-    k_batch_mask<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const uint8_t *)ctx->misc6.p, n, batch, b.zsprod, zh, b.scalars + 8 * (1 + n));
-    ctx->launches += 4;
-    std::vector<uint8_t> status(nb);
-    CUDA_TRY(ctx, cudaMemcpyAsync(status.data(), ctx->misc6.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 3;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ss));
+    trace_mark(ctx, "batch status and small-order parts done (decompress stream)", ss);
+    bool all_ok = false;
+    if ((rc = verify_equation(ctx, b, n, nkeys, 0, n, &all_ok))) return rc;
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    std::vector<uint8_t> status(nb);                                     // (a pageable read-back blocks the host: only now)
+    CUDA_TRY(ctx, cudaMemcpyAsync(status.data(), ctx->misc6.p, nb, cudaMemcpyDeviceToHost, ss));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ss));
+    float first_kernel_ms = elapsed_ms(ctx->ev_a, ctx->ev_b);
     std::vector<uint8_t> eq_ok(nb, 0);
     // ranges of batches still to be classified; `known_bad`: the range is known to contain a failing batch (its parent
     // failed and its sibling verified), so its own equation need not be evaluated again
     struct Range { size_t k0, k1; bool known_bad; };
-    std::vector<Range> todo{{0, nb, false}};
+    std::vector<Range> todo;
+    if (all_ok) {
+        std::fill(eq_ok.begin(), eq_ok.end(), (uint8_t)1);
+    } else {
+        k_batch_mask<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const uint8_t *)ctx->misc6.p, n, batch, b.zsprod, zh, b.scalars + 8 * (1 + n));
+        ctx->launches++;
+        todo.push_back({0, nb, false});
+    }
     while (!todo.empty()) {
         const Range r = todo.back();
         todo.pop_back();
@@ -883,7 +902,7 @@ static int verify_batches_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t 
     }
     {   // stage timings of the call, as in verify_tail (the first equation's bucket kernel; the R decompression of every piece)
         float ms = 0.f;
-        if ((ms = elapsed_ms(ctx->ev_a, ctx->ev_b)) >= 0.f) ctx->last_kernel_ms = ms;
+        if (first_kernel_ms >= 0.f) ctx->last_kernel_ms = first_kernel_ms;
         ctx->last_prep_ms = 0.f;
         for (int k = 0; k < ctx->prep_pieces; k++)
             if ((ms = elapsed_ms(ctx->ev_prep[k][0], ctx->ev_prep[k][1])) >= 0.f) ctx->last_prep_ms += ms;
