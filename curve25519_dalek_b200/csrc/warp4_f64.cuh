@@ -186,11 +186,32 @@ W4_DEV void w4f_horner(w4f_point &tot, const ge_p3_raw *windows, int ranks, int 
     fe64 d2; fe64_const_2d(d2);
     w4f_point x;
     w4f_identity(tot);
+    // Leading windows that are empty contribute nothing and doubling the identity is wasted latency: the top window of
+    // every MSM over canonical scalars (< 2^253) is the carry window of the signed recoding, always empty; short scalars
+    // (verify_batch's 128-bit z_i) leave more.  `started` is uniform over the warp (every lane loads the same points).
+    bool started = false;
 #pragma unroll 1
     for (int w = nwin - 1; w >= 0; w--) {
-        if (w != nwin - 1) {
+        if (started) {
 #pragma unroll 1
             for (int k = 0; k < c; k++) w4f_dbl(tot, role, k == c - 1);
+        } else {
+            bool any = false;
+#pragma unroll 1
+            for (int r = 0; r < ranks; r++) {
+                ge_p3 q; ge_p3_raw raw;
+#if defined(__CUDA_ARCH__)
+                const uint4 *s4 = reinterpret_cast<const uint4 *>(windows + (size_t)r * nwin + w);
+#pragma unroll
+                for (int k = 0; k < 10; k++) { uint4 v = s4[k]; raw.w[4 * k] = v.x; raw.w[4 * k + 1] = v.y; raw.w[4 * k + 2] = v.z; raw.w[4 * k + 3] = v.w; }
+#else
+                raw = windows[(size_t)r * nwin + w];
+#endif
+                ge_p3_load_raw(q, raw);
+                any |= !ge_is_identity(q);
+            }
+            if (!any) continue;
+            started = true;
         }
 #pragma unroll 1
         for (int r = 0; r < ranks; r++) { w4f_load(x, windows + (size_t)r * nwin + w); w4f_add(tot, x, d2, role); }
