@@ -175,3 +175,52 @@ def test_mixed_order_batches_have_z_dependent_verdicts(oracle):
         # every signature is individually INVALID under `verify` only when its own defect is non-zero: the clean ones pass
         assert oracle.verify(msgs[1], sigs[1], pks[1]) in (0, 1)
     assert verdicts == {0, 1} and disagreements > 0
+
+
+def test_small_order_part_of_a_batch_equation_from_scalars_mod_8(oracle):
+    """The identity behind the engine's per-batch small-order test (csrc/batch.cu, k_batch_torsion): with E the value of the
+    batch equation (batch.rs:240-244), S = sum (z_i mod 8) R_i + sum ((z_i h_i mod l) mod 8) A_i and the digits
+    k = a + 3 b (a, b in {-1, 0, 1}) the kernel uses,
+        [l] S == identity   <=>   the small-order part of E is zero,
+    and E == identity (the reference's verdict) <=> [8] E == identity (prime-order part) and [l] S == identity.
+    Checked on the torsion batches of tests/torsion_cases.py, where both outcomes occur, with the oracle's own z_i."""
+    import torsion_cases
+    L = pyref.L
+    lb = L.to_bytes(32, "little")
+    AB = {0: (0, 0), 1: (1, 0), 2: (-1, 1), 3: (0, 1), 4: (1, 1), 5: (0, -1), 6: (1, -1), 7: (-1, 0)}   # k = a + 3 b mod 8
+    assert all((a + 3 * b) % 8 == k for k, (a, b) in AB.items())
+    seen = set()
+    for trial in range(12):
+        n = 24
+        msgs, sigs, pks = torsion_cases.make_batch(oracle, n, seed=77000 + trial)
+        rc, zs = oracle.verify_batch(msgs, sigs, pks, want_zs=True)
+        assert rc in (0, 1)
+        B = oracle.basepoint()
+        E, B1, B3 = oracle.identity(), oracle.identity(), oracle.identity()
+        sum_zs = 0
+        for i in range(n):
+            z = int.from_bytes(zs[16 * i:16 * i + 16], "little")
+            R, A = oracle.decompress(sigs[i][:32]), oracle.decompress(pks[i])
+            assert R is not None and A is not None
+            h = int.from_bytes(hashlib.sha512(sigs[i][:32] + pks[i] + msgs[i]).digest(), "little") % L
+            zh = z * h % L
+            sum_zs = (sum_zs + z * int.from_bytes(sigs[i][32:], "little")) % L
+            E = oracle.add(E, oracle.scalarmul(z.to_bytes(32, "little"), R))
+            E = oracle.add(E, oracle.scalarmul(zh.to_bytes(32, "little"), A))
+            for k, P in ((z % 8, R), (zh % 8, A)):
+                a, b = AB[k]
+                if a:
+                    B1 = oracle.add(B1, P) if a > 0 else oracle.sub(B1, P)
+                if b:
+                    B3 = oracle.add(B3, P) if b > 0 else oracle.sub(B3, P)
+        E = oracle.add(E, oracle.scalarmul(((L - sum_zs) % L).to_bytes(32, "little"), B))
+        assert oracle.is_identity(E) == (rc == 0)                         # the reference's verdict is this equation
+        S = oracle.add(B1, oracle.add(oracle.double(B3), B3))             # B1 + 3 B3
+        lS = oracle.scalarmul(lb, S)
+        small_zero = oracle.is_identity(lS)
+        prime_zero = oracle.is_identity(oracle.mul_by_pow_2(E, 3))
+        lE = oracle.scalarmul(lb, E)
+        assert small_zero == oracle.is_identity(lE)                       # [l] S and [l] E are the same small-order test
+        assert (rc == 0) == (prime_zero and small_zero)
+        seen.add((prime_zero, small_zero))
+    assert (True, True) in seen and (True, False) in seen
