@@ -179,6 +179,144 @@ W4_DEV void w4f_to_p3(ge_p3 &o, const w4f_point &p)
 // 2d (u64/constants.rs:54) as balanced doubles
 FE_HD void fe64_const_2d(fe64 &d2) { fe k; fe_const_2d(k); fe64_from_fe_limbs(d2, k); }
 
+// ---- 20-lane doubling chain: the LIMBS of a point spread over lanes -----------------------------------------------
+// A run of doublings without additions (the c doublings between two windows of the Horner pass, 240 of them per MSM, all
+// dependent) is bound by the instruction count of ONE doubling on ONE warp.  In the 4-lane form every lane still runs a
+// whole 25-product field multiplication.  Here lane 5 g + i holds ONE double: limb i of coordinate g (X, Y, Z, T); a field
+// multiplication is then five products per lane (row i of the schoolbook matrix), a transpose-sum over the five lanes of
+// the group with shuffles, and ONE parallel round of carries:
+//     lane i:  U[e] = (lo(a_i b_e) + 2 f(a_i b_{e-1})) * (19 if i + e >= 5),   U[0] = lo(a_i b_0) + 38 f(a_i b_4)
+//     limb k = sum_d U_{lane (k - d) mod 5}[d];   q_k = round(limb_k / 2^51);   limb_k <- limb_k - q_k 2^51 + q_{k-1} (19 q_4)
+// (p = f 2^52 + lo is the exact split of fe64_mul).  |column| < 2^60, so |q| < 2^9 and limbs end within 2^50 + 2^14: scale 1
+// under the operand rule.  About 270 instructions per doubling instead of about 700.  Lanes 20..31 mirror lanes 0..11.
+struct w20_role { uint32_t g, i, base; };
+W4_DEV w20_role w20_roles() { const uint32_t l = w4_lane(); w20_role r; r.g = (l / 5u) & 3u; r.i = l % 5u; r.base = 5u * r.g; return r; }
+
+W4_DEV double w20_shfl(double v, uint32_t src)
+{
+    const long long b = w4_bits(v);
+    const uint32_t lo = w4_shfl((uint32_t)b, (int)src), hi = w4_shfl((uint32_t)((uint64_t)b >> 32), (int)src);
+    return w4_from_bits((long long)(((uint64_t)hi << 32) | lo));
+}
+W4_DEV long long w20_shfl_ll(long long b, uint32_t src)
+{
+    const uint32_t lo = w4_shfl((uint32_t)b, (int)src), hi = w4_shfl((uint32_t)((uint64_t)b >> 32), (int)src);
+    return (long long)(((uint64_t)hi << 32) | lo);
+}
+
+// fe64_carry on a limb-distributed element (every lane of a group holds its limb of the same element)
+W4_DEV double w20_carry(double f, const w20_role &r)
+{
+#if FE64_DEV
+    const double C = 6755399441055744.0;                                 // 1.5 * 2^52
+    const double q = __fma_rn(f, 1.0 / 2251799813685248.0, C) - C;       // round(f / 2^51)
+    const double rr = __fma_rn(q, -2251799813685248.0, f);
+#else
+    const double q = nearbyint(f / 2251799813685248.0), rr = f - q * 2251799813685248.0;
+#endif
+    const double qp = w20_shfl(q, r.base + (r.i + 4u) % 5u);
+    return rr + (r.i == 0 ? 19.0 * qp : qp);
+}
+
+// exact split of one limb product: p = a b = f 2^52 + lo, f = floor(p / 2^52), 0 <= lo < 2^52   (|p| < 2^103)
+W4_DEV void w20_split(long long &f, long long &lo, double a, double b, double b_scaled /* b 2^-52 */)
+{
+#if FE64_DEV
+    const double M1 = 6755399441055744.0;                               // 1.5 * 2^52
+    const double K = 6755399441055744.0 * 4503599627370496.0 + 4503599627370496.0;
+    const double t = __fma_rz(a, b_scaled, M1);
+    const double u = __fma_rn(t, -4503599627370496.0, K);
+    const double l = __fma_rn(a, b, u);
+    f = __double_as_longlong(t) - (FE64_E52 + (1LL << 51));
+    lo = __double_as_longlong(l) - FE64_E52;
+#else
+    (void)b_scaled;
+    const __int128 p = (__int128)(long long)a * (__int128)(long long)b, lim = (__int128)1 << 103;
+    assert(p < lim && p > -lim);
+    f = (long long)(p >> 52);
+    lo = (long long)(p - ((__int128)f << 52));
+#endif
+}
+
+// limb i of A * B from limb i of A and limb i of B (both limb-distributed over the lanes of the group)
+W4_DEV double w20_mul(double a_own, double b_own, const w20_role &r)
+{
+    double b[5];
+#pragma unroll
+    for (uint32_t j = 0; j < 5; j++) b[j] = w20_shfl(b_own, r.base + j);
+    long long f[5], lo[5];
+#pragma unroll
+    for (int d = 0; d < 5; d++) w20_split(f[d], lo[d], a_own, b[d], b[d] * (1.0 / 4503599627370496.0));
+    long long U[5];
+    U[0] = lo[0] + 38 * f[4];
+#pragma unroll
+    for (uint32_t e = 1; e < 5; e++) {
+        const long long v = lo[e] + 2 * f[e - 1];
+        U[e] = r.i + e >= 5u ? 19 * v : v;
+    }
+    long long R = U[0];
+#pragma unroll
+    for (uint32_t d = 1; d < 5; d++) R += w20_shfl_ll(U[d], r.base + (r.i + 5u - d) % 5u);
+    const long long q = (R + (1LL << 50)) >> 51;
+    const long long rr = R - q * (1LL << 51);
+    long long qp = (long long)(int32_t)w4_shfl((uint32_t)(int32_t)q, (int)(r.base + (r.i + 4u) % 5u));
+    if (r.i == 0) qp *= 19;
+    const long long limb = rr + qp;
+#if FE64_DEV
+    return __longlong_as_double((limb + (1LL << 51)) | FE64_E52) - (FE64_TWO52 + FE64_TWO51);
+#else
+    assert(limb < (1LL << 50) + (1LL << 15) && limb > -(1LL << 50) - (1LL << 15));
+    return (double)limb;
+#endif
+}
+
+// own limb of the replicated point / back (c = limb i of coordinate g)
+W4_DEV double w20_take(const w4f_point &p, const w20_role &r)
+{
+    double v = 0.0;
+#pragma unroll
+    for (uint32_t k = 0; k < 5; k++) {
+        const double x = r.g == 0 ? p.X.v[k] : r.g == 1 ? p.Y.v[k] : r.g == 2 ? p.Z.v[k] : p.T.v[k];
+        if (r.i == k) v = x;
+    }
+    return v;
+}
+W4_DEV void w20_give(w4f_point &p, double c)
+{
+#pragma unroll
+    for (uint32_t k = 0; k < 5; k++) {
+        p.X.v[k] = w20_shfl(c, k); p.Y.v[k] = w20_shfl(c, 5u + k); p.Z.v[k] = w20_shfl(c, 10u + k); p.T.v[k] = w20_shfl(c, 15u + k);
+    }
+}
+
+// c <- limb of 2P (curve_models.rs:381-397 + :365-372; the same formulas and scales as w4f_dbl); T is not read
+W4_DEV void w20_dbl(double &c, const w20_role &r)
+{
+    const double x = w20_shfl(c, r.i), y = w20_shfl(c, 5u + r.i);
+    const double s = w20_carry(x + y, r);                               // squaring operand of scale 1
+    const double in = r.g == 3 ? s : c;
+    const double sq = w20_mul(in, in, r);                               // XX, YY, ZZ, (X+Y)^2 in groups 0..3
+    const double xx = w20_shfl(sq, r.i), yy = w20_shfl(sq, 5u + r.i), zz = w20_shfl(sq, 10u + r.i), s2 = w20_shfl(sq, 15u + r.i);
+    const double Yp = yy + xx, Ym = yy - xx;                            // 2, 2
+    const double E = s2 - Yp;                                           // 3
+    const double F = w20_carry(zz + zz - Ym, r);                        // 4 -> 1
+    const double a = r.g == 1 ? Yp : r.g == 2 ? Ym : E;                 // X3 = E F, Y3 = Yp Ym, Z3 = Ym F, T3 = E Yp
+    const double b = r.g == 1 ? Ym : r.g == 3 ? Yp : F;
+    c = w20_mul(a, b, r);                                               // <= 3 x 2
+}
+
+// p <- 2^k p
+W4_DEV void w20_dbl_n(w4f_point &p, int k)
+{
+    const w20_role r = w20_roles();
+    double c = w20_take(p, r);
+#if FE64_DEV
+#pragma unroll 1
+#endif
+    for (int t = 0; t < k; t++) w20_dbl(c, r);
+    w20_give(p, c);
+}
+
 // Horner over windows (pippenger.rs:159): total = total * 2^c + sum over ranks of window w, from the top window down.
 // windows: rank-major (ranks x nwin raw points).  The result is replicated in the four lanes of every group.
 W4_DEV void w4f_horner(w4f_point &tot, const ge_p3_raw *windows, int ranks, int nwin, int c, uint32_t role)
@@ -193,8 +331,7 @@ W4_DEV void w4f_horner(w4f_point &tot, const ge_p3_raw *windows, int ranks, int 
 #pragma unroll 1
     for (int w = nwin - 1; w >= 0; w--) {
         if (started) {
-#pragma unroll 1
-            for (int k = 0; k < c; k++) w4f_dbl(tot, role, k == c - 1);
+            w20_dbl_n(tot, c);
         } else {
             bool any = false;
 #pragma unroll 1
