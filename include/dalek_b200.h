@@ -63,7 +63,7 @@ const char *dalek_b200_last_error(const dalek_b200_ctx *ctx);
  * NOT reference-equivalent on inputs with small-order components), "field_f64" (1 = bucket kernel on the FP64-pipe field,
  * default; 0 = IMAD.WIDE field), "acc_tma" (1 = the bucket kernel gathers points with TMA bulk copies, default 0: cp.async),
  * "small_straus" (1 = fewer than 190 pairs run vartime Straus like the reference, default; 0 = bucket pipeline),
- * "host_chunks" (1..8, host-buffer MSM calls stream their input in this many chunks, default 4), "verify_pieces" (1..8, same
+ * "host_chunks" (1..8, host-buffer MSM calls stream their input in this many chunks, default 8), "verify_pieces" (1..8, same
  * for verify_batch, default 4), "decompress_f64" (1 = square-root exponentiation of decompression on the FP64 field, default),
  * "dedupe_keys" (1 = decompress every distinct public key once and give it one MSM term, default), "double_base_comb" (1 =
  * fixed-base comb for double-base batches of >= 4096 pairs, default), "precomp_tables" (1 = precomputations of >= 4096 points
