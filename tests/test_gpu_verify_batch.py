@@ -361,6 +361,52 @@ def test_verify_batches_large_device(eng, oracle):
     assert eng.verify_batch_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, device_ptrs=True) == VERIFY
 
 
+@pytest.mark.parametrize("dedupe", [1, 0])
+def test_verify_batches_host_pieces(eng, oracle, dedupe):
+    """Host buffers of >= 2^18 signatures are streamed in pieces (copies of piece k+1 under the front end of piece k; keys are
+    de-duplicated across pieces): failures planted in different pieces, a key that only occurs late, a ragged last
+    batch; the same verdicts from device memory and for every piece count; three planted batches against the oracle's
+    verify_batch."""
+    import hashlib
+    import numpy as np
+    import torch
+    n, bs, nk = (1 << 18) + 300, 256, 61
+    seeds_k = np.stack([np.frombuffer(hashlib.sha512(b"p%d" % k).digest()[:32], dtype=np.uint8) for k in range(nk + 1)])
+    idx = np.arange(n) % nk
+    idx[n - 5000:] = np.where(np.arange(5000) % 7 == 0, nk, idx[n - 5000:])       # key nk only occurs in the last piece
+    seeds = np.ascontiguousarray(seeds_k[idx])
+    offs = np.arange(n + 1, dtype=np.uint64) * 59
+    flat = np.random.Generator(np.random.PCG64(9)).integers(0, 256, size=59 * n, dtype=np.uint8)
+    pks, sigs = eng.sign_batch_flat(seeds, flat, offs, n)
+    pk = np.frombuffer(pks, dtype=np.uint8).copy(); sg = np.frombuffer(sigs, dtype=np.uint8).copy()
+    nb = (n + bs - 1) // bs
+    bad = {3: 3 * bs + 17, 400: 400 * bs + 255, 777: 777 * bs, nb - 1: n - 1}      # batch -> corrupted signature
+    for i in bad.values():
+        flat[59 * i + 5] ^= 0x10
+    sg[64 * (600 * bs + 9) + 63] |= 0x80                                           # batch 600: non-canonical s -> ScalarFormat
+    want = [OK] * nb
+    for k in bad:
+        want[k] = VERIFY
+    want[600] = SCALARFMT
+    eng.set_option("dedupe_keys", dedupe)
+    try:
+        for pieces in (4, 3, 8, 1):
+            eng.set_option("verify_pieces", pieces)
+            rc, v = eng.verify_batches_flat(flat, offs, sg.tobytes(), pk.tobytes(), n, bs)
+            assert rc == VERIFY and v == want, pieces
+        dev = torch.device("cuda", 0)
+        d = [torch.from_numpy(x if x.dtype == np.uint8 else x.view(np.int64)).to(dev) for x in (flat, offs, sg, pk)]
+        rc, v = eng.verify_batches_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, bs, device_ptrs=True)
+        assert rc == VERIFY and v == want
+    finally:
+        eng.set_option("verify_pieces", 4)
+        eng.set_option("dedupe_keys", 1)
+    for k in (3, 600, nb - 1):
+        lo, hi = k * bs, min(n, (k + 1) * bs)
+        assert oracle.verify_batch([flat[59 * i:59 * i + 59].tobytes() for i in range(lo, hi)], [sg[64 * i:64 * i + 64].tobytes() for i in range(lo, hi)],
+                                   [pk[32 * i:32 * i + 32].tobytes() for i in range(lo, hi)]) == want[k]
+
+
 def test_verify_batches_all_distinct_keys_with_failure(eng, oracle):
     """Every key different (no merging possible) and one bad batch: the bisection evaluates sub-ranges through the
     per-key accumulation path; exactly that batch must fail, with and without key merging."""
