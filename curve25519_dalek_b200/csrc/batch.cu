@@ -918,6 +918,34 @@ static int verify_batches_tail(dalek_b200_ctx *ctx, const VerifyBufs &b, size_t 
     return any ? ED25519_ERR_VERIFY : DALEK_OK;
 }
 
+// Front end shared with the per-signature verifier (single.cu): SHA-512(R || A || M) mod l and the canonical-s marks of
+// every signature, public keys de-duplicated (rep / dense / uniq as in verify_batch).  Synchronises to return the number
+// of distinct keys.  All arrays live in the context's workspaces until the next verify call.
+int verify_each_front(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t *d_offs, const uint32_t *d_sigs, const uint32_t *d_keys,
+                      size_t n, EachFront *out)
+{
+    int rc;
+    VerifyBufs b;
+    if ((rc = verify_reserve(ctx, n, b))) return rc;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx, cudaMemsetAsync(b.flags, 0, 64, st));
+    if (!ctx->opt_dedupe_keys) {                       // (verify_reserve only clears the table when merging is on)
+        CUDA_TRY(ctx, cudaMemsetAsync(b.table, 0xff, ((size_t)b.tmask + 1) * 4, st));
+        CUDA_TRY(ctx, cudaMemsetAsync(b.counters, 0, 64, st));
+    }
+    k_hram<<<cdiv(n, 128), 128, 0, st>>>(d_msgs, d_offs, d_sigs, d_keys, n, b.hrams, b.hs, b.flags, b.bad_s);
+    k_key_dedupe<<<cdiv(n, 256), 256, 0, st>>>(d_keys, 0, n, b.table, b.tmask, b.rep, b.uniq, b.dense, b.counters,
+                                               make_uint4(ctx->hash_seed[0], ctx->hash_seed[1], ctx->hash_seed[2], ctx->hash_seed[3]));
+    ctx->launches += 2;
+    if ((rc = pinned_reserve(ctx, 256))) return rc;
+    uint32_t *hk = (uint32_t *)ctx->h_pinned;
+    CUDA_TRY(ctx, cudaMemcpyAsync(hk, b.counters, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    out->hs = b.hs; out->bad_s = b.bad_s; out->rep = b.rep; out->dense = b.dense; out->uniq = b.uniq; out->nkeys = *hk;
+    if (out->nkeys == 0 || out->nkeys > n) { ctx->last_error = "key table corrupted"; return -4; }
+    return 0;
+}
+
 // batch = 0: one verdict (verify_batch); batch > 0: independent batches of that many signatures, verdicts[k] each
 static int verify_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t *d_offs, const uint32_t *d_sigs,
                       const uint32_t *d_keys, size_t n, size_t batch, int32_t *verdicts)

@@ -46,6 +46,7 @@ struct dalek_b200_ctx {
     long opt_acc_tma = 0;       // bucket kernel gathers points with TMA bulk copies + mbarriers instead of cp.async (A/B option)
     long opt_transcript_warp = 1; // up to 2048 Merlin transcripts per launch run one WARP each (25-lane Keccak); 0 = one thread each
     long opt_transcript_blocks = 1; // more transcripts than that: one THREAD each with the rate block staged in shared memory (0 = byte-wise sponge)
+    long opt_each_comb = 1;     // verify_each (non-strict): 1 = per-key comb tables when every key signs >= 8 signatures on average, 2 = always, 0 = never
     long opt_small_straus = 1;  // fewer than 190 pairs: vartime Straus (3 launches) instead of the bucket pipeline
     long opt_field_f64 = 1;     // bucket kernel on the FP64 pipe (fe64.cuh) instead of IMAD.WIDE (fe.cuh)
     // timing of the dominant kernel in the last call
@@ -55,11 +56,12 @@ struct dalek_b200_ctx {
     bool async_open = false;       // a ..._partial_async call is in flight: its device span ends in ..._combine_dev
     // device workspaces (grown on demand, reused across calls)
     DevBuf scalars, points_in, points, digits, counts, offsets, sorted, buckets, red_a, red_b, red_c,
-        red_d, key_pts, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums, msg_offs, sum_desc, sum_part, key_table, key_acc, task_order, sig_status, misc6;
+        red_d, key_pts, result, flags, misc0, misc1, misc2, misc3, misc4, misc5, zs, base_table, ntasks, task_off, tasks, task_sums, msg_offs, sum_desc, sum_part, key_table, key_acc, task_order, sig_status, misc6, each_pow, each_tab, each_kstat;
     const uint64_t *key_points = nullptr;   // device: callers' decompressed key points for the current verify_batch call (or null)
     uint32_t hash_seed[4] = {0x243F6A88u, 0x85A308D3u, 0x13198A2Eu, 0x03707344u};   // key of the public-key de-duplication hash, redrawn per context
     int sum_desc_c = -1;
     bool base_table_ready = false;
+    bool each_attr_set = false;     // the same for k_verify_each_comb
     bool comb_attr_set = false;     // cudaFuncAttributeMaxDynamicSharedMemorySize set for the comb kernel on this device
     // pinned host staging
     void *h_pinned = nullptr;
@@ -168,6 +170,11 @@ int msm_partial_enqueue_record(dalek_b200_ctx *ctx, const void *scalars, const v
 // `ranks` records (host or device, rec_bytes apart) -> per-window sums, Horner, encode; blocks for the result.
 int msm_combine_records(dalek_b200_ctx *ctx, const void *records, bool on_device, size_t rec_bytes, int ranks, size_t n_shard,
                         uint8_t out_compressed[32], uint64_t out_limbs[20]);
+
+// ---- front end of verify_batch reused by the per-signature verifier (batch.cu -> single.cu) ----
+struct EachFront { const uint32_t *hs; const uint8_t *bad_s; const uint32_t *rep, *dense, *uniq; size_t nkeys; };
+int verify_each_front(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t *d_offs, const uint32_t *d_sigs, const uint32_t *d_keys,
+                      size_t n, EachFront *out);
 
 // ---- variable-time Straus for small inputs (straus_vt.cu): the reference's path below 190 points ----
 #define STRAUS_VT_THRESHOLD 190            // edwards.rs:1025-1029

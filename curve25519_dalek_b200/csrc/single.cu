@@ -153,6 +153,186 @@ static int verify_each_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uin
     return 0;
 }
 
+// ---- keys that sign many signatures: per-key comb tables ----------------------------------------------------------
+// R' = [s]B - [k]A costs 252 doublings because A is only known when the call arrives.  When the batch holds few distinct
+// keys (a validator set, an exchange's hot keys: bench.py's 2^22 signatures come from 1024 keys), the doublings can be
+// paid once per KEY: with the 64 x 8 multiples (j+1) 16^i A of every distinct key in device memory (the fixed-base table
+// of B has the same shape), [s]B - [k]A = sum_i s_i (16^i B) - k_i (16^i A) over radix-16 signed digits is 128 mixed
+// additions and no doubling -- the comb of k_double_base_comb (straus.cu) with one table gathered per signature.  Same
+// group element as the reference's vartime_double_scalar_mul_basepoint, hence the same encoding and verdict; keys are
+// de-duplicated, decompressed and tabulated once per call (16 KiB x 4 = 64 KiB of table per key: 1024 keys stay in L2).
+#define EACH_ENT 16                     // doubles per table entry: y+x | y-x | 2dxy as balanced limbs, padded to 128 bytes
+#define EACH_KEY_DOUBLES (64 * 8 * EACH_ENT)
+
+// one thread per distinct key: decompress, 16^i A for i = 0..63 (63 x 4 doublings), small-order mark
+__global__ void __launch_bounds__(64)
+k_each_key_pow16(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ uniq, size_t nkeys, ge_p3_raw *__restrict__ pw,
+                 uint8_t *__restrict__ kstat)
+{
+    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nkeys) return;
+    const size_t i = uniq[slot];
+    uint32_t Ak[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) Ak[k] = keys[8 * i + k];
+    ge_p3 A;
+    fe_1(A.Z);
+    const uint32_t ok = ge_decompress_affine<1>(A.X, A.Y, Ak);             // verifying.rs:167-175
+    if (!ok) { fe_0(A.X); fe_1(A.Y); }
+    fe_mul(A.T, A.X, A.Y);
+    kstat[slot] = (uint8_t)((ok ? 0 : 1) | (is_small_order(A) ? 2 : 0));
+    ge64_p3 P; ge64_from_p3(P, A);
+#pragma unroll 1
+    for (int pos = 0; pos < 64; pos++) {
+        if (pos) { ge64_dbl(P, P); ge64_dbl(P, P); ge64_dbl(P, P); ge64_dbl(P, P); }
+        ge_p3 q; ge64_to_p3(q, P);
+        ge_p3_raw r; ge_p3_store_raw(r, q);
+        uint4 *o = reinterpret_cast<uint4 *>(pw + slot * 64 + pos);
+#pragma unroll
+        for (int w = 0; w < 10; w++) o[w] = make_uint4(r.w[4 * w], r.w[4 * w + 1], r.w[4 * w + 2], r.w[4 * w + 3]);
+    }
+}
+
+// one thread per table entry: (j+1) 16^i A as affine Niels coordinates in balanced FP64 limbs
+__global__ void __launch_bounds__(128)
+k_each_key_rows(const ge_p3_raw *__restrict__ pw, size_t nkeys, double *__restrict__ tab)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nkeys * 512) return;
+    const int j = (int)(t & 7);
+    ge_p3 P;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(pw + (t >> 3));
+        ge_p3_raw r;
+#pragma unroll
+        for (int w = 0; w < 10; w++) { uint4 v = src[w]; r.w[4 * w] = v.x; r.w[4 * w + 1] = v.y; r.w[4 * w + 2] = v.z; r.w[4 * w + 3] = v.w; }
+        ge_p3_load_raw(P, r);
+    }
+    ge_pniels nb; ge_p3_to_pniels(nb, P);
+    ge_p3 Q = P;
+#pragma unroll 1
+    for (int k = 0; k < j; k++) ge_padd(Q, Q, nb, 0);                      // (j+1) * 16^i A
+    fe zi, x, y;
+    fe_invert_f64(zi, Q.Z);
+    fe_mul(x, Q.X, zi); fe_mul(y, Q.Y, zi);
+    ge_niels nl; ge_affine_to_niels(nl, x, y);
+    fe64 e[3];
+    fe64_from_fe(e[0], nl.ypx); fe64_from_fe(e[1], nl.ymx); fe64_from_fe(e[2], nl.xy2d);
+    double *dst = tab + t * EACH_ENT;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int k = 0; k < 5; k++) dst[5 * c + k] = e[c].v[k];
+    dst[15] = 0.0;
+}
+
+// one thread per signature: 64 additions from B's table (shared memory) and 64 from the key's table (L2), compress, compare
+__global__ void __launch_bounds__(128)
+k_verify_each_comb(const uint32_t *__restrict__ sigs, const uint32_t *__restrict__ hs, const uint8_t *__restrict__ bad_s,
+                   const uint32_t *__restrict__ rep, const uint32_t *__restrict__ dense, const uint8_t *__restrict__ kstat,
+                   const double *__restrict__ tab, const ge_niels_packed *__restrict__ base_table, size_t i0, size_t n, uint8_t *__restrict__ out)
+{
+    extern __shared__ double s_B[];                                        // 64 x 8 x 15: (j+1) 16^i B as balanced limbs
+    for (int e = threadIdx.x; e < 512; e += blockDim.x) {
+        ge64_niels q; ge64_niels_unpack(q, base_table[e]);
+        fe64 c;
+        double *dst = s_B + 15 * e;
+        fe64_carry(c, q.ypx);  for (int k = 0; k < 5; k++) dst[k] = c.v[k];
+        fe64_carry(c, q.ymx);  for (int k = 0; k < 5; k++) dst[5 + k] = c.v[k];
+        fe64_carry(c, q.xy2d); for (int k = 0; k < 5; k++) dst[10 + k] = c.v[k];
+    }
+    __syncthreads();
+    const size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t R[8], s[8], h[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { R[k] = sigs[16 * i + k]; s[k] = sigs[16 * i + 8 + k]; h[k] = hs[8 * i + k]; }
+    const uint32_t okS = !bad_s[i];
+    if (!okS) {                                                            // keep the digits in range; the verdict is fixed below
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = 0;
+    }
+    const uint32_t slot = dense[rep[i]];
+    const uint32_t ks = kstat[slot];
+    const double2 *TA = reinterpret_cast<const double2 *>(tab + (size_t)slot * EACH_KEY_DOUBLES);
+    ge64_p3 acc; ge64_identity(acc);
+    int cs = 0, ch = 0;                                                    // radix-16 recoding carries (scalar.rs:1040-1046)
+    uint32_t ws = 0, wh = 0;
+#pragma unroll 1
+    for (int pos = 0; pos < 64; pos++) {
+        if ((pos & 7) == 0) { ws = s[pos >> 3]; wh = h[pos >> 3]; }
+        int dsg = (int)(ws & 15) + cs; ws >>= 4;
+        int dhg = (int)(wh & 15) + ch; wh >>= 4;
+        if (pos < 63) { cs = (dsg + 8) >> 4; dsg -= cs << 4; ch = (dhg + 8) >> 4; dhg -= ch << 4; }
+        // the key's entry first: its L2 latency runs under the addition from B's table
+        double2 a2[8];
+        const int mh = dhg < 0 ? -dhg : dhg;
+        if (mh) {
+            const double2 *src = TA + ((size_t)pos * 8 + (mh - 1)) * (EACH_ENT / 2);
+#pragma unroll
+            for (int k = 0; k < 8; k++) a2[k] = __ldg(src + k);
+        }
+        if (dsg) {
+            const int m = dsg < 0 ? -dsg : dsg;
+            const double *row = s_B + 15 * (8 * pos + (m - 1));
+            ge64_niels q;
+#pragma unroll
+            for (int k = 0; k < 5; k++) { q.ypx.v[k] = row[k]; q.ymx.v[k] = row[5 + k]; q.xy2d.v[k] = row[10 + k]; }
+            ge64_madd(acc, acc, q, (uint32_t)(dsg < 0));
+        }
+        if (mh) {
+            ge64_niels q;
+            q.ypx.v[0] = a2[0].x; q.ypx.v[1] = a2[0].y; q.ypx.v[2] = a2[1].x; q.ypx.v[3] = a2[1].y; q.ypx.v[4] = a2[2].x;
+            q.ymx.v[0] = a2[2].y; q.ymx.v[1] = a2[3].x; q.ymx.v[2] = a2[3].y; q.ymx.v[3] = a2[4].x; q.ymx.v[4] = a2[4].y;
+            q.xy2d.v[0] = a2[5].x; q.xy2d.v[1] = a2[5].y; q.xy2d.v[2] = a2[6].x; q.xy2d.v[3] = a2[6].y; q.xy2d.v[4] = a2[7].x;
+            ge64_madd(acc, acc, q, (uint32_t)(dhg > 0));                   // minus [k] A: positive digits subtract
+        }
+    }
+    ge_p3 Rc; ge64_to_p3(Rc, acc);
+    uint32_t enc[8];
+    ge_compress<1>(enc, Rc);                                               // RCompute::finish, verifying.rs:553-556
+    uint32_t diff = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) diff |= enc[k] ^ R[k];
+    uint8_t v = ED25519_ERR_VERIFY;
+    if (ks & 1) v = ED25519_ERR_POINT_DECOMPRESSION;
+    else if (!okS) v = ED25519_ERR_SCALAR_FORMAT;
+    else if (diff == 0) v = DALEK_OK;
+    out[i] = v;
+}
+
+// Non-strict verification of n signatures (device inputs) through per-key comb tables; *used = 0 if the keys do not repeat
+// enough (or the tables would not fit) and the caller should run k_verify_each instead.
+static int verify_each_comb(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t *d_offs, const uint32_t *d_sigs,
+                            const uint32_t *d_keys, size_t n, uint8_t *d_out, bool *used)
+{
+    *used = false;
+    if (!n || !ctx->opt_each_comb || !ctx->opt_field_f64) return 0;
+    int rc;
+    EachFront f;
+    if ((rc = verify_each_front(ctx, d_msgs, d_offs, d_sigs, d_keys, n, &f))) return rc;
+    const size_t tab_bytes = f.nkeys * EACH_KEY_DOUBLES * sizeof(double);
+    if (tab_bytes > ((size_t)8 << 30)) return 0;
+    if (ctx->opt_each_comb == 1 && f.nkeys * 8 > n) return 0;             // a table costs about what eight plain verifications cost
+    cudaStream_t st = ctx->stream;
+    if ((rc = ws_reserve(ctx, ctx->each_pow, f.nkeys * 64 * sizeof(ge_p3_raw)))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->each_tab, tab_bytes))) return rc;
+    if ((rc = ws_reserve(ctx, ctx->each_kstat, f.nkeys))) return rc;
+    k_each_key_pow16<<<cdiv(f.nkeys, 64), 64, 0, st>>>(d_keys, f.uniq, f.nkeys, (ge_p3_raw *)ctx->each_pow.p, (uint8_t *)ctx->each_kstat.p);
+    k_each_key_rows<<<cdiv(f.nkeys * 512, 128), 128, 0, st>>>((const ge_p3_raw *)ctx->each_pow.p, f.nkeys, (double *)ctx->each_tab.p);
+    const size_t smem = 512 * 15 * sizeof(double);
+    if (!ctx->each_attr_set) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_verify_each_comb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->each_attr_set = true;
+    }
+    k_verify_each_comb<<<cdiv(n, 128), 128, smem, st>>>(d_sigs, f.hs, f.bad_s, f.rep, f.dense, (const uint8_t *)ctx->each_kstat.p,
+                                                       (const double *)ctx->each_tab.p, (const ge_niels_packed *)ctx->base_table.p, 0, n, d_out);
+    ctx->launches += 3;
+    CUDA_TRY(ctx, cudaGetLastError());
+    *used = true;
+    return 0;
+}
+
 extern "C" {
 
 int ed25519_b200_verify_each_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_flat, const void *d_msg_offsets, const void *d_sigs,
@@ -164,8 +344,11 @@ int ed25519_b200_verify_each_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_fl
     int rc;
     if ((rc = base_table_ensure(ctx))) return rc;
     if ((rc = ws_reserve(ctx, ctx->misc6, std::max<size_t>(1, n)))) return rc;
-    if ((rc = verify_each_dev(ctx, (const uint8_t *)d_msgs_flat, (const uint64_t *)d_msg_offsets, (const uint32_t *)d_sigs,
-                              (const uint32_t *)d_pubkeys, n, strict, (uint8_t *)ctx->misc6.p, ctx->stream))) return rc;
+    bool comb = false;
+    if (!strict && (rc = verify_each_comb(ctx, (const uint8_t *)d_msgs_flat, (const uint64_t *)d_msg_offsets, (const uint32_t *)d_sigs,
+                                          (const uint32_t *)d_pubkeys, n, (uint8_t *)ctx->misc6.p, &comb))) return rc;
+    if (!comb && (rc = verify_each_dev(ctx, (const uint8_t *)d_msgs_flat, (const uint64_t *)d_msg_offsets, (const uint32_t *)d_sigs,
+                                       (const uint32_t *)d_pubkeys, n, strict, (uint8_t *)ctx->misc6.p, ctx->stream))) return rc;
     if (n) CUDA_TRY(ctx, cudaMemcpyAsync(results, ctx->misc6.p, n, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     uint8_t any = 0;
@@ -190,6 +373,23 @@ int ed25519_b200_verify_each_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat,
     if ((rc = ws_reserve(ctx, ctx->misc6, std::max<size_t>(1, n)))) return rc;
     uint8_t *d_msgs = (uint8_t *)ctx->misc1.p, *d_sigs = (uint8_t *)ctx->points_in.p, *d_keys = d_sigs + n * 64, *d_out = (uint8_t *)ctx->misc6.p;
     uint64_t *d_offs = (uint64_t *)ctx->msg_offs.p;
+    if (!strict && ctx->opt_each_comb && ctx->opt_field_f64 && n) {
+        // keys may repeat: everything crosses PCIe first (the key tables need every key), then either the comb path or,
+        // when the keys turn out not to repeat, the plain kernel on the resident copies
+        cudaStream_t st = ctx->stream;
+        if (mbytes) CUDA_TRY(ctx, cudaMemcpyAsync(d_msgs, msgs_flat, mbytes, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_offs, msg_offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_sigs, sigs, n * 64, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_keys, pubkeys, n * 32, cudaMemcpyHostToDevice, st));
+        bool comb = false;
+        if ((rc = verify_each_comb(ctx, d_msgs, d_offs, (const uint32_t *)d_sigs, (const uint32_t *)d_keys, n, d_out, &comb))) return rc;
+        if (!comb && (rc = verify_each_dev(ctx, d_msgs, d_offs, (const uint32_t *)d_sigs, (const uint32_t *)d_keys, n, strict, d_out, st))) return rc;
+        CUDA_TRY(ctx, cudaMemcpyAsync(results, d_out, n, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        uint8_t any = 0;
+        for (size_t i = 0; i < n; i++) any |= results[i];
+        return any ? ED25519_ERR_VERIFY : DALEK_OK;
+    }
     // independent per signature: pieces alternate between two streams (copy-in -> kernel -> copy-out)
     cudaStream_t ss[2] = {ctx->stream, ctx->stream2};
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));

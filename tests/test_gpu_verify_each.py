@@ -99,3 +99,64 @@ def test_verify_each_agrees_with_batch_and_locates_failures(eng, oracle):
     for i in bad[:2]:
         m = fl[int(offs[i]):int(offs[i + 1])].tobytes()
         assert oracle.verify(m, sg[64 * i:64 * i + 64].tobytes(), pk[32 * i:32 * i + 32].tobytes()) == res[i]
+
+
+@pytest.mark.parametrize("mode", [2, 0])
+def test_comb_path_on_reference_fixtures(eng, oracle, mode):
+    """The per-key comb tables of the non-strict path (option each_comb: 2 = always, 0 = never, 1 = when keys repeat >= 8
+    times on average) must give the verdicts of the plain kernel and of the oracle on every reference fixture: the 914
+    VALIDATIONVECTORS (small-order and mixed-order keys, non-canonical encodings), the TESTVECTORS with one failure of every
+    kind, from host and from device buffers."""
+    import numpy as np
+    import torch
+    with open(os.path.join(ROOT, "tests", "golden", "ed25519_validation.json")) as f:
+        vec = json.load(f)["vectors"]
+    with open(os.path.join(ROOT, "tests", "golden", "ed25519_testvectors.json")) as f:
+        tv = json.load(f)["vectors"]
+    msgs = [v["msg"].encode() for v in vec] + [H(v["msg"]) for v in tv]
+    sigs = [H(v["sig"]) for v in vec] + [H(v["sig"]) for v in tv]
+    keys = [H(v["key"]) for v in vec] + [H(v["pk"]) for v in tv]
+    n0 = len(vec)
+    msgs[n0 + 3] += b"x"
+    x = bytearray(sigs[n0 + 10]); x[63] |= 0xf0; sigs[n0 + 10] = bytes(x)
+    keys[n0 + 20] = (2).to_bytes(32, "little")
+    sigs[n0 + 40] = (2).to_bytes(32, "little") + sigs[n0 + 40][32:]
+    # every signature three times: keys repeat
+    msgs, sigs, keys = msgs * 3, sigs * 3, keys * 3
+    n = len(msgs)
+    fl, offs = flat(msgs)
+    want = [oracle.verify(m, s, k) for m, s, k in zip(msgs[:n // 3], sigs[:n // 3], keys[:n // 3])] * 3
+    eng.set_option("each_comb", mode)
+    try:
+        rc, res = eng.verify_each_flat(fl, offs, b"".join(sigs), b"".join(keys), n)
+        assert res == want and rc == VERIFY
+        dev = torch.device("cuda", 0)
+        d = [torch.from_numpy(x_).to(dev) for x_ in (fl, offs.view(np.int64), np.frombuffer(b"".join(sigs), dtype=np.uint8).copy(),
+                                                    np.frombuffer(b"".join(keys), dtype=np.uint8).copy())]
+        rc, res = eng.verify_each_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, device_ptrs=True)
+        assert res == want and rc == VERIFY
+    finally:
+        eng.set_option("each_comb", 1)
+
+
+def test_comb_path_large_repeated_keys(eng, oracle):
+    """2^16 signatures by 37 keys (the automatic choice takes the comb path): all valid; planted failures are exactly the ones
+    reported, with the oracle's error kinds."""
+    import numpy as np
+    n, nk = 1 << 16, 37
+    seeds_k = np.stack([np.frombuffer(hashlib.sha512(b"c%d" % k).digest()[:32], dtype=np.uint8) for k in range(nk)])
+    seeds = np.ascontiguousarray(seeds_k[np.arange(n) % nk])
+    offs = np.arange(n + 1, dtype=np.uint64) * 40
+    fl = np.random.Generator(np.random.PCG64(18)).integers(0, 256, size=40 * n, dtype=np.uint8)
+    pks, sigs = eng.sign_batch_flat(seeds, fl, offs, n)
+    pk = np.frombuffer(pks, dtype=np.uint8).copy(); sg = np.frombuffer(sigs, dtype=np.uint8).copy()
+    rc, res = eng.verify_each_flat(fl, offs, sg, pk, n)
+    assert rc == OK and not any(res)
+    bad = [0, 777, 40000, n - 1]
+    for i in bad:
+        fl[40 * i + 7] ^= 0x20
+    sg[64 * 1234 + 63] |= 0xf0                                       # ScalarFormat
+    rc, res = eng.verify_each_flat(fl, offs, sg, pk, n)
+    assert rc == VERIFY and [i for i, r in enumerate(res) if r] == sorted(bad + [1234])
+    for i in (0, 1234):
+        assert res[i] == oracle.verify(fl[40 * i:40 * i + 40].tobytes(), sg[64 * i:64 * i + 64].tobytes(), pk[32 * i:32 * i + 32].tobytes())
