@@ -226,11 +226,22 @@ k_each_key_rows(const ge_p3_raw *__restrict__ pw, size_t nkeys, double *__restri
     dst[15] = 0.0;
 }
 
+// The y coordinates of the eight points of small order (identity, order 2, order 4 twice, order 8 four times), canonical:
+// 1, -1, 0, y8, -y8 (constants::EIGHT_TORSION, u64/constants.rs:196-340).  verify_strict rejects a signature whose R is one of
+// them (verifying.rs:366-376); once the encodings of R' and R agree, R's bytes are canonical and a comparison of bytes decides.
+__constant__ uint32_t c_small_y[5][8] = {
+    {0x00000001u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u},
+    {0xffffffecu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0x7fffffffu},
+    {0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u},
+    {0x706a17c7u, 0x4fd84d3du, 0x760b3cbau, 0x0f67100du, 0xfa53202au, 0xc6cc392cu, 0x77fdc74eu, 0x7a03ac92u},
+    {0x8f95e826u, 0xb027b2c2u, 0x89f4c345u, 0xf098eff2u, 0x05acdfd5u, 0x3933c6d3u, 0x880238b1u, 0x05fc536du}};
+
 // one thread per signature: 64 additions from B's table (shared memory) and 64 from the key's table (L2), compress, compare
 __global__ void __launch_bounds__(128)
 k_verify_each_comb(const uint32_t *__restrict__ sigs, const uint32_t *__restrict__ hs, const uint8_t *__restrict__ bad_s,
                    const uint32_t *__restrict__ rep, const uint32_t *__restrict__ dense, const uint8_t *__restrict__ kstat,
-                   const double *__restrict__ tab, const ge_niels_packed *__restrict__ base_table, size_t i0, size_t n, uint8_t *__restrict__ out)
+                   const double *__restrict__ tab, const ge_niels_packed *__restrict__ base_table, size_t i0, size_t n, int strict,
+                   uint8_t *__restrict__ out)
 {
     extern __shared__ double s_B[];                                        // 64 x 8 x 15: (j+1) 16^i B as balanced limbs
     for (int e = threadIdx.x; e < 512; e += blockDim.x) {
@@ -294,17 +305,28 @@ k_verify_each_comb(const uint32_t *__restrict__ sigs, const uint32_t *__restrict
     uint32_t diff = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) diff |= enc[k] ^ R[k];
+    uint32_t small = 0;
+    if (strict) {                                                          // verifying.rs:366-376: R or A of small order
+        small = (ks >> 1) & 1u;
+#pragma unroll 1
+        for (int t = 0; t < 5; t++) {
+            uint32_t d = (R[7] & 0x7fffffffu) ^ c_small_y[t][7];
+#pragma unroll
+            for (int k = 0; k < 7; k++) d |= R[k] ^ c_small_y[t][k];
+            small |= (uint32_t)(d == 0);
+        }
+    }
     uint8_t v = ED25519_ERR_VERIFY;
     if (ks & 1) v = ED25519_ERR_POINT_DECOMPRESSION;
     else if (!okS) v = ED25519_ERR_SCALAR_FORMAT;
-    else if (diff == 0) v = DALEK_OK;
+    else if (diff == 0 && !small) v = DALEK_OK;
     out[i] = v;
 }
 
-// Non-strict verification of n signatures (device inputs) through per-key comb tables; *used = 0 if the keys do not repeat
+// Verification (verify or verify_strict) of n signatures (device inputs) through per-key comb tables; *used = 0 if the keys do not repeat
 // enough (or the tables would not fit) and the caller should run k_verify_each instead.
 static int verify_each_comb(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uint64_t *d_offs, const uint32_t *d_sigs,
-                            const uint32_t *d_keys, size_t n, uint8_t *d_out, bool *used)
+                            const uint32_t *d_keys, size_t n, int strict, uint8_t *d_out, bool *used)
 {
     *used = false;
     if (!n || !ctx->opt_each_comb || !ctx->opt_field_f64) return 0;
@@ -326,7 +348,7 @@ static int verify_each_comb(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const ui
         ctx->each_attr_set = true;
     }
     k_verify_each_comb<<<cdiv(n, 128), 128, smem, st>>>(d_sigs, f.hs, f.bad_s, f.rep, f.dense, (const uint8_t *)ctx->each_kstat.p,
-                                                       (const double *)ctx->each_tab.p, (const ge_niels_packed *)ctx->base_table.p, 0, n, d_out);
+                                                       (const double *)ctx->each_tab.p, (const ge_niels_packed *)ctx->base_table.p, 0, n, strict, d_out);
     ctx->launches += 3;
     CUDA_TRY(ctx, cudaGetLastError());
     *used = true;
@@ -345,8 +367,8 @@ int ed25519_b200_verify_each_flat_dev(dalek_b200_ctx *ctx, const void *d_msgs_fl
     if ((rc = base_table_ensure(ctx))) return rc;
     if ((rc = ws_reserve(ctx, ctx->misc6, std::max<size_t>(1, n)))) return rc;
     bool comb = false;
-    if (!strict && (rc = verify_each_comb(ctx, (const uint8_t *)d_msgs_flat, (const uint64_t *)d_msg_offsets, (const uint32_t *)d_sigs,
-                                          (const uint32_t *)d_pubkeys, n, (uint8_t *)ctx->misc6.p, &comb))) return rc;
+    if ((rc = verify_each_comb(ctx, (const uint8_t *)d_msgs_flat, (const uint64_t *)d_msg_offsets, (const uint32_t *)d_sigs,
+                               (const uint32_t *)d_pubkeys, n, strict, (uint8_t *)ctx->misc6.p, &comb))) return rc;
     if (!comb && (rc = verify_each_dev(ctx, (const uint8_t *)d_msgs_flat, (const uint64_t *)d_msg_offsets, (const uint32_t *)d_sigs,
                                        (const uint32_t *)d_pubkeys, n, strict, (uint8_t *)ctx->misc6.p, ctx->stream))) return rc;
     if (n) CUDA_TRY(ctx, cudaMemcpyAsync(results, ctx->misc6.p, n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -373,7 +395,7 @@ int ed25519_b200_verify_each_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat,
     if ((rc = ws_reserve(ctx, ctx->misc6, std::max<size_t>(1, n)))) return rc;
     uint8_t *d_msgs = (uint8_t *)ctx->misc1.p, *d_sigs = (uint8_t *)ctx->points_in.p, *d_keys = d_sigs + n * 64, *d_out = (uint8_t *)ctx->misc6.p;
     uint64_t *d_offs = (uint64_t *)ctx->msg_offs.p;
-    if (!strict && ctx->opt_each_comb && ctx->opt_field_f64 && n) {
+    if (ctx->opt_each_comb && ctx->opt_field_f64 && n) {
         // keys may repeat: everything crosses PCIe first (the key tables need every key), then either the comb path or,
         // when the keys turn out not to repeat, the plain kernel on the resident copies
         cudaStream_t st = ctx->stream;
@@ -382,7 +404,7 @@ int ed25519_b200_verify_each_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat,
         CUDA_TRY(ctx, cudaMemcpyAsync(d_sigs, sigs, n * 64, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaMemcpyAsync(d_keys, pubkeys, n * 32, cudaMemcpyHostToDevice, st));
         bool comb = false;
-        if ((rc = verify_each_comb(ctx, d_msgs, d_offs, (const uint32_t *)d_sigs, (const uint32_t *)d_keys, n, d_out, &comb))) return rc;
+        if ((rc = verify_each_comb(ctx, d_msgs, d_offs, (const uint32_t *)d_sigs, (const uint32_t *)d_keys, n, strict, d_out, &comb))) return rc;
         if (!comb && (rc = verify_each_dev(ctx, d_msgs, d_offs, (const uint32_t *)d_sigs, (const uint32_t *)d_keys, n, strict, d_out, st))) return rc;
         CUDA_TRY(ctx, cudaMemcpyAsync(results, d_out, n, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));

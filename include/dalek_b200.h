@@ -70,7 +70,7 @@ const char *dalek_b200_last_error(const dalek_b200_ctx *ctx);
  * also keep the 2^(cw) P window tables; default 0: measured, the 1.7 GB of randomly gathered table entries cost the bucket
  * kernel what the shorter tail saves), "transcript_warp" (1 = launches of up to 2048 Merlin transcripts run one warp each,
  * default), "transcript_blocks" (1 = larger launches run one thread per transcript with the rate block staged in shared
- * memory, default; 0 = byte-wise sponge), "each_comb" (per-signature verification, non-strict: 1 = per-key comb tables when
+ * memory, default; 0 = byte-wise sponge), "each_comb" (per-signature verification: 1 = per-key comb tables when
  * every distinct key signs at least eight signatures on average, default; 2 = always; 0 = never), "trace" (1 = per-stage
  * device timeline of verify_batch on stderr).
  * Returns 0 or DALEK_E_INVALID_ARG. */

@@ -103,7 +103,7 @@ def test_verify_each_agrees_with_batch_and_locates_failures(eng, oracle):
 
 @pytest.mark.parametrize("mode", [2, 0])
 def test_comb_path_on_reference_fixtures(eng, oracle, mode):
-    """The per-key comb tables of the non-strict path (option each_comb: 2 = always, 0 = never, 1 = when keys repeat >= 8
+    """The per-key comb tables (option each_comb: 2 = always, 0 = never, 1 = when keys repeat >= 8
     times on average) must give the verdicts of the plain kernel and of the oracle on every reference fixture: the 914
     VALIDATIONVECTORS (small-order and mixed-order keys, non-canonical encodings), the TESTVECTORS with one failure of every
     kind, from host and from device buffers."""
@@ -125,16 +125,17 @@ def test_comb_path_on_reference_fixtures(eng, oracle, mode):
     msgs, sigs, keys = msgs * 3, sigs * 3, keys * 3
     n = len(msgs)
     fl, offs = flat(msgs)
-    want = [oracle.verify(m, s, k) for m, s, k in zip(msgs[:n // 3], sigs[:n // 3], keys[:n // 3])] * 3
     eng.set_option("each_comb", mode)
     try:
-        rc, res = eng.verify_each_flat(fl, offs, b"".join(sigs), b"".join(keys), n)
-        assert res == want and rc == VERIFY
-        dev = torch.device("cuda", 0)
-        d = [torch.from_numpy(x_).to(dev) for x_ in (fl, offs.view(np.int64), np.frombuffer(b"".join(sigs), dtype=np.uint8).copy(),
-                                                    np.frombuffer(b"".join(keys), dtype=np.uint8).copy())]
-        rc, res = eng.verify_each_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, device_ptrs=True)
-        assert res == want and rc == VERIFY
+        for strict in (False, True):
+            want = [oracle.verify(m, s, k, strict=strict) for m, s, k in zip(msgs[:n // 3], sigs[:n // 3], keys[:n // 3])] * 3
+            rc, res = eng.verify_each_flat(fl, offs, b"".join(sigs), b"".join(keys), n, strict=strict)
+            assert res == want and rc == VERIFY, strict
+            dev = torch.device("cuda", 0)
+            d = [torch.from_numpy(x_).to(dev) for x_ in (fl, offs.view(np.int64), np.frombuffer(b"".join(sigs), dtype=np.uint8).copy(),
+                                                        np.frombuffer(b"".join(keys), dtype=np.uint8).copy())]
+            rc, res = eng.verify_each_flat(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, strict=strict, device_ptrs=True)
+            assert res == want and rc == VERIFY, strict
     finally:
         eng.set_option("each_comb", 1)
 
