@@ -1022,6 +1022,11 @@ def main():
             # one verdict per signature (VerifyingKey::verify semantics: R' recomputed and compared as bytes)
             v4 = run_verify(args, rank, world, local, eng=eng, steps=2, warmup=1, each=True)
             line["verify_each"] = {k: v4[k] for k in ("value", "unit", "ms_per_step", "e2e")}
+            line["verify_each"]["path"] = ("1024 distinct keys: per-key comb tables (64 x 8 multiples of every key resident in L2), "
+                                           "128 mixed additions and no doubling per signature")
+            # every key different: nothing to tabulate, the 252-doubling double-scalar multiplication per signature
+            v5 = run_verify(args, rank, world, local, eng=eng, steps=1, warmup=1, each=True, nkeys=1 << 30)
+            line["verify_each"]["all_distinct_keys"] = {k: v5[k] for k in ("value", "unit", "ms_per_step", "e2e")}
             pool = CpuPool(1)
             m_, s_, k_ = pool.verify_inputs(2048)
             cdt = pool.verify_each(m_, s_, k_, 2048)

@@ -161,6 +161,7 @@ static int verify_each_dev(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const uin
 // additions and no doubling -- the comb of k_double_base_comb (straus.cu) with one table gathered per signature.  Same
 // group element as the reference's vartime_double_scalar_mul_basepoint, hence the same encoding and verdict; keys are
 // de-duplicated, decompressed and tabulated once per call (16 KiB x 4 = 64 KiB of table per key: 1024 keys stay in L2).
+#define EACH_K 4                        // signatures per thread of the comb kernel: one shared inversion
 #define EACH_ENT 16                     // doubles per table entry: y+x | y-x | 2dxy as balanced limbs, padded to 128 bytes
 #define EACH_KEY_DOUBLES (64 * 8 * EACH_ENT)
 
@@ -237,7 +238,7 @@ __constant__ uint32_t c_small_y[5][8] = {
     {0x8f95e826u, 0xb027b2c2u, 0x89f4c345u, 0xf098eff2u, 0x05acdfd5u, 0x3933c6d3u, 0x880238b1u, 0x05fc536du}};
 
 // one thread per signature: 64 additions from B's table (shared memory) and 64 from the key's table (L2), compress, compare
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 k_verify_each_comb(const uint32_t *__restrict__ sigs, const uint32_t *__restrict__ hs, const uint8_t *__restrict__ bad_s,
                    const uint32_t *__restrict__ rep, const uint32_t *__restrict__ dense, const uint8_t *__restrict__ kstat,
                    const double *__restrict__ tab, const ge_niels_packed *__restrict__ base_table, size_t i0, size_t n, int strict,
@@ -253,74 +254,95 @@ k_verify_each_comb(const uint32_t *__restrict__ sigs, const uint32_t *__restrict
         fe64_carry(c, q.xy2d); for (int k = 0; k < 5; k++) dst[10 + k] = c.v[k];
     }
     __syncthreads();
-    const size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t R[8], s[8], h[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) { R[k] = sigs[16 * i + k]; s[k] = sigs[16 * i + 8 + k]; h[k] = hs[8 * i + k]; }
-    const uint32_t okS = !bad_s[i];
-    if (!okS) {                                                            // keep the digits in range; the verdict is fixed below
-#pragma unroll
-        for (int k = 0; k < 8; k++) s[k] = 0;
-    }
-    const uint32_t slot = dense[rep[i]];
-    const uint32_t ks = kstat[slot];
-    const double2 *TA = reinterpret_cast<const double2 *>(tab + (size_t)slot * EACH_KEY_DOUBLES);
-    ge64_p3 acc; ge64_identity(acc);
-    int cs = 0, ch = 0;                                                    // radix-16 recoding carries (scalar.rs:1040-1046)
-    uint32_t ws = 0, wh = 0;
+    // EACH_K consecutive signatures per thread: their EACH_K inversions (the x / Z, y / Z of the encodings) become one, by
+    // the simultaneous-inversion pattern of field.rs:239-273 -- 265 field operations per signature become 265 / 4 + 3
+    const size_t first = i0 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * EACH_K;
+    if (first >= n) return;
+    fe PX[EACH_K], PY[EACH_K], PZ[EACH_K], pre[EACH_K];
+    uint8_t pending[EACH_K];
 #pragma unroll 1
-    for (int pos = 0; pos < 64; pos++) {
-        if ((pos & 7) == 0) { ws = s[pos >> 3]; wh = h[pos >> 3]; }
-        int dsg = (int)(ws & 15) + cs; ws >>= 4;
-        int dhg = (int)(wh & 15) + ch; wh >>= 4;
-        if (pos < 63) { cs = (dsg + 8) >> 4; dsg -= cs << 4; ch = (dhg + 8) >> 4; dhg -= ch << 4; }
-        // the key's entry first: its L2 latency runs under the addition from B's table
-        double2 a2[8];
-        const int mh = dhg < 0 ? -dhg : dhg;
-        if (mh) {
-            const double2 *src = TA + ((size_t)pos * 8 + (mh - 1)) * (EACH_ENT / 2);
+    for (int q = 0; q < EACH_K; q++) {
+        const size_t i = first + q;
+        if (i >= n) { fe_0(PX[q]); fe_1(PY[q]); fe_1(PZ[q]); pending[q] = 0xff; continue; }
+        uint32_t s[8], h[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) a2[k] = __ldg(src + k);
-        }
-        if (dsg) {
-            const int m = dsg < 0 ? -dsg : dsg;
-            const double *row = s_B + 15 * (8 * pos + (m - 1));
-            ge64_niels q;
+        for (int k = 0; k < 8; k++) { s[k] = sigs[16 * i + 8 + k]; h[k] = hs[8 * i + k]; }
+        const uint32_t okS = !bad_s[i];
+        if (!okS) {                                                        // keep the digits in range; the verdict is fixed below
 #pragma unroll
-            for (int k = 0; k < 5; k++) { q.ypx.v[k] = row[k]; q.ymx.v[k] = row[5 + k]; q.xy2d.v[k] = row[10 + k]; }
-            ge64_madd(acc, acc, q, (uint32_t)(dsg < 0));
+            for (int k = 0; k < 8; k++) s[k] = 0;
         }
-        if (mh) {
-            ge64_niels q;
-            q.ypx.v[0] = a2[0].x; q.ypx.v[1] = a2[0].y; q.ypx.v[2] = a2[1].x; q.ypx.v[3] = a2[1].y; q.ypx.v[4] = a2[2].x;
-            q.ymx.v[0] = a2[2].y; q.ymx.v[1] = a2[3].x; q.ymx.v[2] = a2[3].y; q.ymx.v[3] = a2[4].x; q.ymx.v[4] = a2[4].y;
-            q.xy2d.v[0] = a2[5].x; q.xy2d.v[1] = a2[5].y; q.xy2d.v[2] = a2[6].x; q.xy2d.v[3] = a2[6].y; q.xy2d.v[4] = a2[7].x;
-            ge64_madd(acc, acc, q, (uint32_t)(dhg > 0));                   // minus [k] A: positive digits subtract
-        }
-    }
-    ge_p3 Rc; ge64_to_p3(Rc, acc);
-    uint32_t enc[8];
-    ge_compress<1>(enc, Rc);                                               // RCompute::finish, verifying.rs:553-556
-    uint32_t diff = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) diff |= enc[k] ^ R[k];
-    uint32_t small = 0;
-    if (strict) {                                                          // verifying.rs:366-376: R or A of small order
-        small = (ks >> 1) & 1u;
+        const uint32_t slot = dense[rep[i]];
+        const uint32_t ks = kstat[slot];
+        const double2 *TA = reinterpret_cast<const double2 *>(tab + (size_t)slot * EACH_KEY_DOUBLES);
+        ge64_p3 acc; ge64_identity(acc);
+        int cs = 0, ch = 0;                                                // radix-16 recoding carries (scalar.rs:1040-1046)
+        uint32_t ws = 0, wh = 0;
 #pragma unroll 1
-        for (int t = 0; t < 5; t++) {
-            uint32_t d = (R[7] & 0x7fffffffu) ^ c_small_y[t][7];
+        for (int pos = 0; pos < 64; pos++) {
+            if ((pos & 7) == 0) { ws = s[pos >> 3]; wh = h[pos >> 3]; }
+            int dsg = (int)(ws & 15) + cs; ws >>= 4;
+            int dhg = (int)(wh & 15) + ch; wh >>= 4;
+            if (pos < 63) { cs = (dsg + 8) >> 4; dsg -= cs << 4; ch = (dhg + 8) >> 4; dhg -= ch << 4; }
+            // the key's entry first: its L2 latency runs under the addition from B's table
+            double2 a2[8];
+            const int mh = dhg < 0 ? -dhg : dhg;
+            if (mh) {
+                const double2 *src = TA + ((size_t)pos * 8 + (mh - 1)) * (EACH_ENT / 2);
 #pragma unroll
-            for (int k = 0; k < 7; k++) d |= R[k] ^ c_small_y[t][k];
-            small |= (uint32_t)(d == 0);
+                for (int k = 0; k < 8; k++) a2[k] = __ldg(src + k);
+            }
+            if (dsg) {
+                const int m = dsg < 0 ? -dsg : dsg;
+                const double *row = s_B + 15 * (8 * pos + (m - 1));
+                ge64_niels qn;
+#pragma unroll
+                for (int k = 0; k < 5; k++) { qn.ypx.v[k] = row[k]; qn.ymx.v[k] = row[5 + k]; qn.xy2d.v[k] = row[10 + k]; }
+                ge64_madd(acc, acc, qn, (uint32_t)(dsg < 0));
+            }
+            if (mh) {
+                ge64_niels qn;
+                qn.ypx.v[0] = a2[0].x; qn.ypx.v[1] = a2[0].y; qn.ypx.v[2] = a2[1].x; qn.ypx.v[3] = a2[1].y; qn.ypx.v[4] = a2[2].x;
+                qn.ymx.v[0] = a2[2].y; qn.ymx.v[1] = a2[3].x; qn.ymx.v[2] = a2[3].y; qn.ymx.v[3] = a2[4].x; qn.ymx.v[4] = a2[4].y;
+                qn.xy2d.v[0] = a2[5].x; qn.xy2d.v[1] = a2[5].y; qn.xy2d.v[2] = a2[6].x; qn.xy2d.v[3] = a2[6].y; qn.xy2d.v[4] = a2[7].x;
+                ge64_madd(acc, acc, qn, (uint32_t)(dhg > 0));               // minus [k] A: positive digits subtract
+            }
         }
+        ge_p3 Rc; ge64_to_p3(Rc, acc);
+        PX[q] = Rc.X; PY[q] = Rc.Y; PZ[q] = Rc.Z;
+        pending[q] = (uint8_t)((ks & 1) ? ED25519_ERR_POINT_DECOMPRESSION : !okS ? ED25519_ERR_SCALAR_FORMAT : ((strict && (ks & 2)) ? ED25519_ERR_VERIFY : 0));
     }
-    uint8_t v = ED25519_ERR_VERIFY;
-    if (ks & 1) v = ED25519_ERR_POINT_DECOMPRESSION;
-    else if (!okS) v = ED25519_ERR_SCALAR_FORMAT;
-    else if (diff == 0 && !small) v = DALEK_OK;
-    out[i] = v;
+    // 1 / Z of the EACH_K points with one inversion (Z is never zero: the formulas are complete)
+    fe run; fe_copy(run, PZ[0]);
+#pragma unroll 1
+    for (int q = 1; q < EACH_K; q++) { fe_copy(pre[q], run); fe_mul(run, run, PZ[q]); }
+    fe inv; fe_invert_f64(inv, run);
+#pragma unroll 1
+    for (int q = EACH_K - 1; q >= 0; q--) {
+        fe zi;
+        if (q) { fe_mul(zi, inv, pre[q]); fe_mul(inv, inv, PZ[q]); } else fe_copy(zi, inv);
+        const size_t i = first + q;
+        if (i >= n) continue;
+        fe x, y;
+        fe_mul(x, PX[q], zi); fe_mul(y, PY[q], zi);
+        uint32_t enc[8];
+        fe_tobytes_words(enc, y);                                          // RCompute::finish, verifying.rs:553-556 (EdwardsPoint::compress)
+        enc[7] ^= (uint32_t)fe_isnegative(x) << 31;
+        uint32_t R[8], diff = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { R[k] = sigs[16 * i + k]; diff |= enc[k] ^ R[k]; }
+        uint32_t small = 0;
+        if (strict) {                                                      // verifying.rs:366-376: R of small order (A: per key, above)
+#pragma unroll 1
+            for (int t = 0; t < 5; t++) {
+                uint32_t d = (R[7] & 0x7fffffffu) ^ c_small_y[t][7];
+#pragma unroll
+                for (int k = 0; k < 7; k++) d |= R[k] ^ c_small_y[t][k];
+                small |= (uint32_t)(d == 0);
+            }
+        }
+        out[i] = pending[q] ? pending[q] : (uint8_t)((diff == 0 && !small) ? DALEK_OK : ED25519_ERR_VERIFY);
+    }
 }
 
 // Verification (verify or verify_strict) of n signatures (device inputs) through per-key comb tables; *used = 0 if the keys do not repeat
@@ -347,7 +369,7 @@ static int verify_each_comb(dalek_b200_ctx *ctx, const uint8_t *d_msgs, const ui
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_verify_each_comb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->each_attr_set = true;
     }
-    k_verify_each_comb<<<cdiv(n, 128), 128, smem, st>>>(d_sigs, f.hs, f.bad_s, f.rep, f.dense, (const uint8_t *)ctx->each_kstat.p,
+    k_verify_each_comb<<<cdiv((n + EACH_K - 1) / EACH_K, 128), 128, smem, st>>>(d_sigs, f.hs, f.bad_s, f.rep, f.dense, (const uint8_t *)ctx->each_kstat.p,
                                                        (const double *)ctx->each_tab.p, (const ge_niels_packed *)ctx->base_table.p, 0, n, strict, d_out);
     ctx->launches += 3;
     CUDA_TRY(ctx, cudaGetLastError());
