@@ -261,8 +261,8 @@ int dalek_b200_ristretto_vartime_msm(dalek_b200_ctx *ctx, const uint8_t *scalars
  * (E/batch.rs:208-250): non-canonical s -> ED25519_ERR_SCALAR_FORMAT; undecodable R or a
  * non-identity result -> ED25519_ERR_VERIFY; else 0.  No cofactor multiplication.
  * Coefficients z_i: exactly the reference's -- ONE Merlin transcript over the whole batch (batch.rs:168-222), whatever n
- * is.  That transcript is a strictly sequential sponge (1.73 Keccak-f[1600] permutations per signature, one GPU thread:
- * about 1 ms per 100 signatures), so callers with very large inputs either use ed25519_b200_verify_batches_flat (independent
+ * is.  That transcript is a strictly sequential sponge (1.73 Keccak-f[1600] permutations per signature, one GPU warp:
+ * about 12 us per signature), so callers with very large inputs either use ed25519_b200_verify_batches_flat (independent
  * batches, each with the reference's transcript, hashed in parallel) or OPT INTO the option "verify_chunk" = k > 0: one
  * transcript per k consecutive signatures and one combined equation.  The chunked mode is NOT reference-equivalent: its z_i
  * differ from the reference's for n > k, and while the verdict is the same for every batch without small-order components
@@ -321,6 +321,9 @@ int ed25519_b200_verify_batches_flat_points_dev(dalek_b200_ctx *ctx, const void 
  * returns for signature i alone: 0 Ok, 1 Verify, 3 ScalarFormat, 4 PointDecompression.  R' = [s]B - [k]A is
  * recomputed (RCompute, E/verifying.rs:496-557) and its ENCODING compared with the signature's R bytes, so --
  * unlike verify_batch -- a non-canonical R is rejected; verify_strict also rejects small-order R or A.
+ * When the batch holds few distinct keys (every key signing at least eight signatures on average; option "each_comb") the
+ * 64 x 8 multiples (j+1) 16^i A of every distinct key are tabulated once per call and each signature costs 128 mixed
+ * additions and no doubling; otherwise every signature pays its own 252 doublings.  Same results either way.
  * Returns 0 if every result is 0, 1 otherwise; negative on engine errors.  results: n bytes (host). */
 int ed25519_b200_verify_each_flat(dalek_b200_ctx *ctx, const uint8_t *msgs_flat, const uint64_t *msg_offsets,
                                   const uint8_t *sigs, const uint8_t *pubkeys, size_t n, int strict,
