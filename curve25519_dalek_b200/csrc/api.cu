@@ -144,10 +144,17 @@ static int run_msm(dalek_b200_ctx *ctx, const void *scalars, const void *points_
     // (straus_vt.cu) instead of the ~27 of the bucket pipeline; only for whole MSMs (a shard must yield window sums)
     const bool straus = d_result && n == n_window && n < STRAUS_VT_THRESHOLD && ctx->opt_small_straus && ctx->opt_field_f64;
     if (on_device) {
-        if ((rc = msm_prepare_points(ctx, points_in, point_fmt, n, ctx->points.p, (int *)ctx->flags.p))) return rc;
         if (straus) {
+            if ((rc = msm_prepare_points(ctx, points_in, point_fmt, n, ctx->points.p, (int *)ctx->flags.p))) return rc;
             if ((rc = straus_vartime_msm(ctx, (const uint32_t *)scalars, ctx->points.p, kind, n, d_result))) return rc;
-        } else if ((rc = msm_accumulate_chunk(ctx, (const uint32_t *)scalars, ctx->points.p, kind, n, c, true))) return rc;
+        } else {
+            // the point conversion (or decompression) runs on the second stream under the digit / sort passes of the main one
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+            if ((rc = msm_prepare_points_on(ctx, ctx->stream2, points_in, point_fmt, n, ctx->points.p, (int *)ctx->flags.p))) return rc;
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+            if ((rc = msm_accumulate_chunk(ctx, (const uint32_t *)scalars, ctx->points.p, kind, n, c, true, 0, 0, ctx->ev_join))) return rc;
+        }
     } else {
         if ((rc = ws_reserve(ctx, ctx->scalars, std::max<size_t>(1, n) * 32))) return rc;
         if ((rc = ws_reserve(ctx, ctx->points_in, std::max<size_t>(1, n) * pin))) return rc;

@@ -150,8 +150,10 @@ int msm_window_sums(dalek_b200_ctx *ctx, const uint32_t *d_scalars /* n x 8 word
 // limbs51 (20 u64) + identity flag to d_result (layout: 8 u32 | pad | 20 u64 | u32 flag).
 struct MsmResult { uint32_t compressed[8]; uint64_t limbs[20]; uint32_t is_identity; uint32_t pad; };
 // building blocks: one chunk of pairs into the buckets; then reduction (+ Horner + encode if d_result)
+// points_ready (optional): an event after which d_points may be read -- the digit and sort passes do not wait for it
 int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n,
-                         int c, bool first, int active_windows = 0, size_t flat = 0);
+                         int c, bool first, int active_windows = 0, size_t flat = 0, cudaEvent_t points_ready = nullptr);
+int msm_prepare_points_on(dalek_b200_ctx *ctx, cudaStream_t st, const void *d_in, int point_fmt, size_t n, void *d_out, int *d_bad);
 // window width for `n_short` scalars of `short_bits` bits plus `n_long` full-width scalars (verify_batch)
 int msm_choose_window_bits_mixed(const dalek_b200_ctx *ctx, size_t n_short, int short_bits, size_t n_long);
 int msm_reduce_finish(dalek_b200_ctx *ctx, int c, ge_p3_raw *d_windows, MsmResult *d_result, bool flat = false);

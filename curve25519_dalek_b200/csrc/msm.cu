@@ -97,18 +97,23 @@ __global__ void k_prep_extended(const uint64_t *__restrict__ in, ge_pniels_packe
     for (int k = 0; k < 8; k++) o[k] = make_uint4(pk.w[4 * k], pk.w[4 * k + 1], pk.w[4 * k + 2], pk.w[4 * k + 3]);
 }
 
-int msm_prepare_points(dalek_b200_ctx *ctx, const void *d_in, int point_fmt, size_t n, void *d_out, int *d_bad)
+int msm_prepare_points_on(dalek_b200_ctx *ctx, cudaStream_t st, const void *d_in, int point_fmt, size_t n, void *d_out, int *d_bad)
 {
     if (n == 0) return 0;
     if (point_fmt == DALEK_POINTS_COMPRESSED) {
-        if (ctx->opt_decompress_f64) k_prep_compressed<1><<<cdiv(n, 128), 128, 0, ctx->stream>>>((const uint4 *)d_in, (ge_niels_packed *)d_out, n, d_bad);
-        else k_prep_compressed<0><<<cdiv(n, 128), 128, 0, ctx->stream>>>((const uint4 *)d_in, (ge_niels_packed *)d_out, n, d_bad);
+        if (ctx->opt_decompress_f64) k_prep_compressed<1><<<cdiv(n, 128), 128, 0, st>>>((const uint4 *)d_in, (ge_niels_packed *)d_out, n, d_bad);
+        else k_prep_compressed<0><<<cdiv(n, 128), 128, 0, st>>>((const uint4 *)d_in, (ge_niels_packed *)d_out, n, d_bad);
     } else {
-        k_prep_extended<<<cdiv(n, 128), 128, 0, ctx->stream>>>((const uint64_t *)d_in, (ge_pniels_packed *)d_out, n);
+        k_prep_extended<<<cdiv(n, 128), 128, 0, st>>>((const uint64_t *)d_in, (ge_pniels_packed *)d_out, n);
     }
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
+}
+
+int msm_prepare_points(dalek_b200_ctx *ctx, const void *d_in, int point_fmt, size_t n, void *d_out, int *d_bad)
+{
+    return msm_prepare_points_on(ctx, ctx->stream, d_in, point_fmt, n, d_out, d_bad);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -712,7 +717,7 @@ k_combine(const ge_p3_raw *__restrict__ windows, int ranks, int nwin, int c, Msm
 // bucket window, so the reduction handles 2^(c-1) buckets instead of nwin times as many and no doubling is left
 // (pair with msm_reduce_finish(..., flat = true)).
 int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const void *d_points, int point_kind, size_t n,
-                         int c, bool first, int active_windows, size_t flat)
+                         int c, bool first, int active_windows, size_t flat, cudaEvent_t points_ready)
 {
     const int nwin_d = msm_window_count_for_bits(c);               // digit windows
     const int nact = active_windows > 0 && active_windows < nwin_d ? active_windows : nwin_d;
@@ -775,6 +780,8 @@ int msm_accumulate_chunk(dalek_b200_ctx *ctx, const uint32_t *d_scalars, const v
             ctx->launches++;
         }
     }
+    // the digit / sort passes above only read the scalars: the conversion of the points may still be running on another stream
+    if (points_ready) CUDA_TRY(ctx, cudaStreamWaitEvent(st, points_ready, 0));
     if (first) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st));
     {
         const unsigned grid = cdiv(max_tasks, 128);
