@@ -121,6 +121,62 @@ int h_straus_vartime(uint8_t *out, const uint8_t *scalars, const uint8_t *points
     return 1;
 }
 
+// The 20-lane field multiplication (w20_mul: one limb per lane, transpose-sum by shuffles, one parallel round of carries)
+// against the single-thread host model fe64_mul, compared as canonical bytes.  a, b: 4 x 5 limbs each (one element per lane
+// group), integer-valued doubles chosen by the caller -- incl. the operand-rule extremes (|a_i b_j| just below 2^103).
+// Returns 1 if all four products agree and every output limb is within scale 1.
+int h_w20_mul(const double *a, const double *b)
+{
+    double out[32];
+    run_warp([&](uint32_t lane) {
+        const w20_role r = w20_roles();
+        out[lane] = w20_mul(a[5 * r.g + r.i], b[5 * r.g + r.i], r);
+    });
+    for (int g = 0; g < 4; g++) {
+        fe64 x, y, want, got;
+        for (int k = 0; k < 5; k++) { x.v[k] = a[5 * g + k]; y.v[k] = b[5 * g + k]; got.v[k] = out[5 * g + k]; }
+        fe64_mul(want, x, y);
+        fe64_assert_scale(got, 1.0);
+        fe fw, fg; fe64_to_fe(fw, want); fe64_to_fe(fg, got);
+        uint32_t bw[8], bg[8]; fe_tobytes_words(bw, fw); fe_tobytes_words(bg, fg);
+        if (memcmp(bw, bg, 32)) return 0;
+    }
+    for (int l = 20; l < 32; l++) if (out[l] != out[l - 20]) return -1;             // lanes 20..31 mirror lanes 0..11
+    return 1;
+}
+
+// w20_carry (a limb-distributed fe64_carry) on four elements at once
+int h_w20_carry(const double *a)
+{
+    double out[32];
+    run_warp([&](uint32_t lane) { const w20_role r = w20_roles(); out[lane] = w20_carry(a[5 * r.g + r.i], r); });
+    for (int g = 0; g < 4; g++) {
+        fe64 x, want;
+        for (int k = 0; k < 5; k++) x.v[k] = a[5 * g + k];
+        fe64_carry(want, x);
+        for (int k = 0; k < 5; k++) if (want.v[k] != out[5 * g + k]) return 0;
+    }
+    return 1;
+}
+
+// k doublings of one point on 20 lanes (w20_dbl_n) -> compressed
+int h_w20_dbl_n(uint8_t *out, const uint8_t *point, int k)
+{
+    ge_p3 p, q; if (!load_point(p, point)) return 0;
+    blind(q, p);
+    ge_p3_raw raw; ge_p3_store_raw(raw, q);
+    std::vector<uint8_t> outs(32 * 32);
+    run_warp([&](uint32_t lane) {
+        w4f_point t; w4f_load(t, &raw);
+        w20_dbl_n(t, k);
+        ge_p3 r; w4f_to_p3(r, t);
+        store_point(&outs[32 * lane], r);
+    });
+    for (int l = 1; l < 32; l++) if (memcmp(&outs[0], &outs[32 * l], 32)) return -1;
+    memcpy(out, &outs[0], 32);
+    return 1;
+}
+
 // NAF digits of one scalar (NAF_LEN of them)
 void h_naf5(int8_t *out, const uint8_t *scalar) { uint32_t s[8]; memcpy(s, scalar, 32); naf5(out, s); }
 

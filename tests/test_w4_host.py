@@ -115,3 +115,50 @@ def test_warp_transcript_draws_the_reference_coefficients(w4, oracle, n):
     out = (C.c_uint8 * (16 * n))()
     w4.h_merlin_zs(out, hr, b"".join(sigs), C.c_uint64(n))
     assert bytes(out) == want
+
+
+def test_20_lane_field_multiplication_at_the_operand_rule_extremes(w4):
+    """w20_mul / w20_carry (one limb per lane: the doublings of the Horner pass) against the single-thread model: random
+    balanced limbs and the corners of the operand rule -- scales 3 x 2, 2 x 2, 1 x 4 + the 2^15 slack, every limb at +- the
+    bound, single non-zero limbs -- so that every column sum and every carry of the parallel round sees its extreme."""
+    rnd = random.Random(20)
+    B = 1 << 50
+    dbl = C.c_double * 20
+    w4.h_w20_mul.argtypes = [dbl, dbl]
+    w4.h_w20_carry.argtypes = [dbl]
+
+    def limbs(scale, mode):
+        lim = scale * B + (scale << 14)
+        if mode == "rand":
+            return [float(rnd.randrange(-lim, lim + 1)) for _ in range(5)]
+        if mode == "max":
+            return [float(lim)] * 5
+        if mode == "min":
+            return [float(-lim)] * 5
+        if mode == "alt":
+            return [float(lim if k % 2 == 0 else -lim) for k in range(5)]
+        v = [0.0] * 5; v[rnd.randrange(5)] = float(rnd.choice((lim, -lim))); return v      # "one"
+
+    modes = ("rand", "max", "min", "alt", "one")
+    for sa, sb in ((1, 1), (2, 2), (3, 2), (2, 3), (1, 4), (1, 7), (7, 1)):
+        for trial in range(40):
+            a, b = [], []
+            for g in range(4):
+                ma, mb = (rnd.choice(modes), rnd.choice(modes)) if trial >= 8 else (modes[(trial + g) % 5], modes[(trial * 3 + g) % 5])
+                a += limbs(sa, ma); b += limbs(sb, mb)
+            assert w4.h_w20_mul(dbl(*a), dbl(*b)) == 1, (sa, sb, trial)
+    for trial in range(200):
+        a = []
+        for g in range(4):
+            a += limbs(rnd.choice((1, 2, 4, 64, 4096)), rnd.choice(modes))
+        assert w4.h_w20_carry(dbl(*a)) == 1, trial
+
+
+@pytest.mark.parametrize("k", [1, 2, 16, 65])
+def test_20_lane_doublings_match_oracle(w4, oracle, k):
+    rnd = random.Random(k)
+    for P in _points(oracle, rnd, 6):
+        out = (C.c_uint8 * 32)()
+        assert w4.h_w20_dbl_n(out, oracle.compress(P), k) == 1
+        assert bytes(out) == oracle.compress(oracle.mul_by_pow_2(P, k))
+
