@@ -279,7 +279,8 @@ def run_msm(args, rank, world, local):
             "config": {"workload": "pippenger_msm", "pairs_total": n_total, "pairs_per_gpu": n_local,
                        "point_format": "extended radix-2^51 limbs (160 B)", "window_bits": c,
                        "l2": "inputs (%.0f MB per GPU) exceed the 126 MB L2" % (algo_bytes / 1e6),
-                       "timing": "value / ms_per_step: K blocking C-ABI calls bracketed by barrier + device sync, max over ranks; "
+                       "host_buffers": "pinned, filled by one thread (NUMA-local first touch)",
+                   "timing": "value / ms_per_step: K blocking C-ABI calls bracketed by barrier + device sync, max over ranks; "
                                  "device_ms_per_step: CUDA events on the engine's stream around each call (rank 0)",
                        "device_ms_per_step": statistics.mean(call_ms), "e2e_device_ms_per_step": statistics.mean(e2e_call_ms),
                        "parity": "algebraic identity sum s_i(t_i B) == (sum s_i t_i)B checked at full size",
@@ -564,6 +565,7 @@ def run_verify(args, rank, world, local, eng=None, steps=None, warmup=None, nkey
                    "keys": "the callers' decompressed points (VerifyingKey, 160 B each) beside the 32-byte encodings" if key_points
                            else "32-byte encodings, decompressed inside the call",
                    "batch_size": batch_size or None,
+                   "host_buffers": "pinned, filled by one thread (NUMA-local first touch)",
                    "timing": "value / ms_per_step: K blocking C-ABI calls bracketed by barrier + device sync, max over ranks; "
                              "device_ms_per_step: CUDA events on the engine's stream around each call (rank 0)",
                    "device_ms_per_step": statistics.mean(call_ms), "e2e_device_ms_per_step": statistics.mean(e2e_call_ms),
@@ -957,6 +959,14 @@ def run_reference(args, rank, world):
 
 # ------------------------------------------------------------------------------------------ main
 def main():
+    # Pinned host buffers are filled by ONE thread, so that their pages sit on one NUMA node (first touch): a buffer filled
+    # by torch's CPU thread pool is spread over both sockets and crosses PCIe at 34.5 GB/s instead of 55.5 GB/s on these boxes
+    # (tools/pcie_probe.py, profiles/pcie_probe_r2.json).  Nothing else in this process uses torch's CPU threads.
+    try:
+        import torch
+        torch.set_num_threads(1)
+    except ImportError:
+        pass
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -3,6 +3,7 @@ and from pinned host buffers (pieces streamed over PCIe), for 1..8 pieces.  Run 
 import sys
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import numpy as np, torch
+torch.set_num_threads(1)            # pinned buffers first-touched by one thread (NUMA-local): 55 instead of 35 GB/s over PCIe
 import curve25519_dalek_b200 as pkg
 import bench
 eng = pkg.Engine(0)
