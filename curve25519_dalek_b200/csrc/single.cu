@@ -8,7 +8,9 @@
 // bytes, so a non-canonical R fails here although it passes the batch equation (ed25519-dalek README,
 // "Validation criteria"); VALIDATIONVECTORS pins both behaviours (tests).
 //
-// One thread per signature.  [s]B + [k](-A) is computed on the FP64 field with radix-16 signed digits
+// Two paths, same results.  When the keys of a call repeat, the doublings are paid once per KEY (per-key comb tables,
+// k_each_key_* and k_verify_each_comb below: 128 mixed additions per signature, no doubling).  Otherwise (plain kernel,
+// k_verify_each): one thread per signature.  [s]B + [k](-A) is computed on the FP64 field with radix-16 signed digits
 // (scalar.rs:1019-1051): 63 x 4 doublings, 64 mixed additions from the shared 8-entry table of B and 64 additions
 // from the thread's own 8-entry table of -A (local memory).  The reference interleaves width-5 / width-8 NAFs;
 // fixed radix-16 keeps the lanes of a warp on the same schedule.  Same group element, hence the same encoding.
